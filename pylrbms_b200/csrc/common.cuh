@@ -1,0 +1,95 @@
+// Shared internals of liblrbms_sm100: context / plan structs, error plumbing, FP64 tensor-core primitive.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/lrbms_sm100.h"
+
+struct lrbms_context {
+  int device = -1;
+  int sm_count = 0;
+  int max_smem_optin = 0;
+  std::string last_error;
+};
+
+enum PlanKind { PLAN_SPMM = 1, PLAN_PROJECT = 2, PLAN_ONLINE = 3 };
+
+struct lrbms_plan {
+  lrbms_context* ctx = nullptr;
+  PlanKind kind;
+  std::vector<void*> device_allocs;   // freed in lrbms_plan_destroy
+  size_t device_bytes = 0;
+  double info_launches = 0, info_ctas = 0, info_bytes = 0, info_flops = 0, info_bytes_survey = 0;
+  virtual ~lrbms_plan() {}
+  virtual int run(void* stream) = 0;
+};
+
+extern thread_local std::string g_create_error;
+
+inline int lrbms_fail(lrbms_context* ctx, int code, const std::string& msg) {
+  if (ctx) ctx->last_error = msg; else g_create_error = msg;
+  return code;
+}
+
+#define LRBMS_CUDA_CHECK(ctx, expr)                                                                  \
+  do {                                                                                               \
+    cudaError_t _e = (expr);                                                                         \
+    if (_e != cudaSuccess) {                                                                         \
+      return lrbms_fail((ctx), LRBMS_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));  \
+    }                                                                                                \
+  } while (0)
+
+#define LRBMS_REQUIRE(ctx, cond, msg)                                             \
+  do {                                                                            \
+    if (!(cond)) return lrbms_fail((ctx), LRBMS_ERR_INVALID, std::string(msg));   \
+  } while (0)
+
+// Allocate device memory owned by a plan.
+template <typename T>
+inline int plan_alloc(lrbms_plan* p, T** out, size_t count) {
+  void* ptr = nullptr;
+  size_t bytes = (count ? count : 1) * sizeof(T);
+  cudaError_t e = cudaMalloc(&ptr, bytes);
+  if (e != cudaSuccess) return lrbms_fail(p->ctx, LRBMS_ERR_ALLOC, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+  p->device_allocs.push_back(ptr);
+  p->device_bytes += bytes;
+  *out = reinterpret_cast<T*>(ptr);
+  return 0;
+}
+
+template <typename T>
+inline int plan_upload(lrbms_plan* p, T** out, const std::vector<T>& host) {
+  int rc = plan_alloc(p, out, host.size());
+  if (rc) return rc;
+  if (!host.empty()) {
+    cudaError_t e = cudaMemcpy(*out, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return lrbms_fail(p->ctx, LRBMS_ERR_CUDA, std::string("cudaMemcpy H2D: ") + cudaGetErrorString(e));
+  }
+  return 0;
+}
+
+#ifdef __CUDACC__
+// D(8x8) += A(8x4, row) * B(4x8, col), FP64 tensor core (SASS: DMMA.8x8x4).
+// lane = 4*g + t:  a = A[g][t],  b = B[t][g],  d0 = D[g][2t], d1 = D[g][2t+1].
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+#endif

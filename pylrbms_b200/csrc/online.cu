@@ -1,0 +1,703 @@
+// Online half of the LRBMS hot path: mu-batched assembly + sparse Cholesky + solves of the block-sparse reduced
+// system (K3 + K4), mu-batched estimator quadratic forms (K5) and the eta combine / max reduction.
+//
+// solve_kernel: one CTA per parameter (grid-stride over the batch).  The reduced matrix lives as 8x8 tiles (the
+// DMMA.8x8x4 accumulator shape); the host-side symbolic phase (symbolic.cpp) provides, per tile of L, the list of
+// (L_IK, L_JK) pairs to subtract.  Per tile column J:  phase A -- every warp forms its target tiles
+// A_IJ(mu) - sum_K L_IK L_JK^T in registers with DMMA (A_IJ(mu) = sum_q theta_q(mu) A_q is assembled on the fly,
+// left to right like LincombOperator.assemble), warp 0 factors the diagonal tile and inverts it;  phase B -- every
+// warp multiplies its tiles by L_JJ^{-T} (two DMMAs) and stores them.  The right-hand side rides along as one more
+// tile row (forward substitution fused into the factorisation); the backward substitution runs from shared memory.
+//
+// estimate_kernel: one CTA per (subdomain, tile of 32 parameters).  Every quadratic form x_L^T M x_R of
+// reference estimators.py:71-85 is evaluated for 32 parameters at once as Y = M X_R on DMMA followed by a column dot
+// with X_L; the matrices are read once per 32 parameters instead of once per parameter.
+#include <algorithm>
+#include <cmath>
+
+#include "common.cuh"
+#include "symbolic.h"
+
+namespace {
+
+constexpr int kSolveThreads = 256;
+constexpr int kSolveWarps = kSolveThreads / 32;
+constexpr int kMaxT = 4;   // targets per warp and round kept in registers
+
+struct SolveParams {
+  int32_t n_red, n_pad, ntc, n_tiles, Q, Qf, n_theta, n_a_tiles;
+  const int32_t* col_ptr;
+  const int32_t* row_idx;
+  const int32_t* pair_ptr;
+  const int32_t* pair_a;
+  const int32_t* pair_b;
+  const int32_t* a_map;
+  const double* a_tiles;   // [Q][n_a_tiles][64]
+  const double* rhs;       // [Qf][n_pad]
+  int64_t work_stride;     // doubles of scratch per CTA: (n_tiles + ntc) * 64 tiles + ntc * 64 inverse diagonal tiles
+};
+
+// target tile = A(mu) tile (or rhs row) minus its update pairs; result in DMMA accumulator layout
+__device__ __forceinline__ void form_target(const SolveParams& P, const double* __restrict__ sth, const double* L,
+                                            int slot, int J, int lane, double& c0, double& c1) {
+  const int g = lane >> 2, t = lane & 3;
+  c0 = 0.0;
+  c1 = 0.0;
+  if (slot < P.n_tiles) {
+    const int ai = P.a_map[slot];
+    if (ai >= 0) {
+      const double2* __restrict__ at = reinterpret_cast<const double2*>(P.a_tiles + (int64_t)ai * 64 + g * 8 + 2 * t);
+      const int64_t qs = (int64_t)P.n_a_tiles * 32;   // stride between affine terms in double2
+      double2 v = __ldg(at);
+      c0 = sth[0] * v.x;
+      c1 = sth[0] * v.y;
+      for (int q = 1; q < P.Q; ++q) {
+        v = __ldg(at + q * qs);
+        c0 += sth[q] * v.x;
+        c1 += sth[q] * v.y;
+      }
+    }
+  } else if (g == 0) {
+    // forward-solve row: f(mu)[8J + 2t .. +1] in row 0 of the tile
+    for (int q = 0; q < P.Qf; ++q) {
+      const double* f = P.rhs + (int64_t)q * P.n_pad + 8 * J + 2 * t;
+      c0 += sth[P.Q + q] * __ldg(f);
+      c1 += sth[P.Q + q] * __ldg(f + 1);
+    }
+  }
+  const int p0 = P.pair_ptr[slot], p1 = P.pair_ptr[slot + 1];
+  double n0 = 0.0, n1 = 0.0;   // second accumulator chain: halves the dependent-DMMA latency
+  const int off = g * 8 + t;
+  int p = p0;
+  for (; p + 1 < p1; p += 2) {
+    const double* a = L + (int64_t)P.pair_a[p] * 64 + off;
+    const double* b = L + (int64_t)P.pair_b[p] * 64 + off;
+    const double* a2 = L + (int64_t)P.pair_a[p + 1] * 64 + off;
+    const double* b2 = L + (int64_t)P.pair_b[p + 1] * 64 + off;
+    const double x0 = a[0], x1 = a[4], y0 = b[0], y1 = b[4];
+    const double z0 = a2[0], z1 = a2[4], w0 = b2[0], w1 = b2[4];
+    dmma884(c0, c1, -x0, y0);
+    dmma884(n0, n1, -z0, w0);
+    dmma884(c0, c1, -x1, y1);
+    dmma884(n0, n1, -z1, w1);
+  }
+  if (p < p1) {
+    const double* a = L + (int64_t)P.pair_a[p] * 64 + off;
+    const double* b = L + (int64_t)P.pair_b[p] * 64 + off;
+    const double x0 = a[0], x1 = a[4], y0 = b[0], y1 = b[4];
+    dmma884(c0, c1, -x0, y0);
+    dmma884(c0, c1, -x1, y1);
+  }
+  c0 += n0;
+  c1 += n1;
+}
+
+// X = C * W^T with C in accumulator layout and W = L_JJ^{-1} (row-major 8x8 in shared memory)
+__device__ __forceinline__ void apply_inverse_transpose(const double* __restrict__ sW, int lane, double c0, double c1,
+                                                        double& x0, double& x1) {
+  const int g = lane >> 2, t = lane & 3;
+  x0 = 0.0;
+  x1 = 0.0;
+#pragma unroll
+  for (int kk = 0; kk < 2; ++kk) {
+    const int src = (lane & ~3) | (2 * kk + (t >> 1));
+    const double v0 = __shfl_sync(0xffffffffu, c0, src);
+    const double v1 = __shfl_sync(0xffffffffu, c1, src);
+    const double a = (t & 1) ? v1 : v0;                 // C[g][4kk + t]
+    const double b = sW[g * 8 + 4 * kk + t];            // B[k = 4kk + t][n = g] = W[g][4kk + t]
+    dmma884(x0, x1, a, b);
+  }
+}
+
+__global__ void __launch_bounds__(kSolveThreads, 2)
+solve_kernel(SolveParams P, int64_t n_mu, const double* __restrict__ theta, double* __restrict__ u, int32_t* __restrict__ info,
+             double* __restrict__ work) {
+  extern __shared__ double smem[];
+  double* sx = smem;                      // n_pad: y, then the solution
+  double* sW = sx + P.n_pad;              // 64: inverse of the current diagonal tile
+  double* sS = sW + 64;                   // 64: scratch for the diagonal tile
+  double* sred = sS + 64;                 // kSolveWarps * 8
+  double* sth = sred + kSolveWarps * 8;   // n_theta
+  __shared__ int s_info;
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  double* L = work + (int64_t)blockIdx.x * P.work_stride;
+  double* Winv = L + (int64_t)(P.n_tiles + P.ntc) * 64;
+
+  for (int64_t mu = blockIdx.x; mu < n_mu; mu += gridDim.x) {
+    __syncthreads();
+    for (int q = threadIdx.x; q < P.n_theta; q += kSolveThreads) sth[q] = theta[mu * P.n_theta + q];
+    if (threadIdx.x == 0) s_info = 0;
+    __syncthreads();
+
+    for (int J = 0; J < P.ntc; ++J) {
+      const int cp0 = P.col_ptr[J], cp1 = P.col_ptr[J + 1];
+      const int n_off = cp1 - cp0 - 1 + 1;        // off-diagonal L targets + the rhs target
+      // ---- diagonal tile: warp 0
+      if (warp == 0) {
+        double c0, c1;
+        form_target(P, sth, L, cp0, J, lane, c0, c1);
+        sS[g * 8 + 2 * t] = c0;
+        sS[g * 8 + 2 * t + 1] = c1;
+        __syncwarp();
+        const int i = lane & 7;
+        double a[8], rinv[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] = sS[i * 8 + j];
+        int bad = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          double akk = __shfl_sync(0xffffffffu, a[k], k);
+          if (8 * J + k >= P.n_red) akk = 1.0;                 // padding rows: identity
+          if (!(akk > 0.0)) { if (!bad) bad = 8 * J + k + 1; akk = 1.0; }
+          const double r = rsqrt(akk);
+          rinv[k] = r;
+          const double lik = ((i == k) ? akk : a[k]) * r;
+          a[k] = lik;
+#pragma unroll
+          for (int j = k + 1; j < 8; ++j) {
+            const double ljk = __shfl_sync(0xffffffffu, lik, j);
+            a[j] -= lik * ljk;
+          }
+        }
+        if (bad && lane == 0 && s_info == 0) s_info = bad;
+        __syncwarp();
+        if (lane < 8) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const double v = (j <= i) ? a[j] : 0.0;
+            sS[i * 8 + j] = v;
+            L[(int64_t)cp0 * 64 + i * 8 + j] = v;
+          }
+        }
+        __syncwarp();
+        // inverse: lane j computes column j of W = L^{-1} by forward substitution (uniform code, broadcast reads)
+        const int jc = lane & 7;
+        double w[8];
+#pragma unroll
+        for (int ii = 0; ii < 8; ++ii) {
+          double s = (ii == jc) ? 1.0 : 0.0;
+#pragma unroll
+          for (int k = 0; k < ii; ++k) s -= sS[ii * 8 + k] * w[k];
+          w[ii] = s * rinv[ii];
+        }
+        if (lane < 8) {
+#pragma unroll
+          for (int ii = 0; ii < 8; ++ii) {
+            sW[ii * 8 + jc] = w[ii];
+            Winv[(int64_t)J * 64 + ii * 8 + jc] = w[ii];
+          }
+        }
+      }
+      // ---- off-diagonal targets and the rhs row: warps 1..7, kMaxT per warp and round
+      for (int base = 0; base < n_off; base += (kSolveWarps - 1) * kMaxT) {
+        double c[kMaxT][2];
+        int slot[kMaxT];
+        if (warp > 0) {
+#pragma unroll
+          for (int i = 0; i < kMaxT; ++i) {
+            const int q = base + i * (kSolveWarps - 1) + (warp - 1);
+            slot[i] = -1;
+            if (q < n_off) {
+              slot[i] = (q < n_off - 1) ? (cp0 + 1 + q) : (P.n_tiles + J);
+              form_target(P, sth, L, slot[i], J, lane, c[i][0], c[i][1]);
+            }
+          }
+        }
+        __syncthreads();   // diagonal inverse ready (first round); all targets of this round formed
+        if (warp > 0) {
+#pragma unroll
+          for (int i = 0; i < kMaxT; ++i) {
+            if (slot[i] >= 0) {
+              double x0, x1;
+              apply_inverse_transpose(sW, lane, c[i][0], c[i][1], x0, x1);
+              *reinterpret_cast<double2*>(L + (int64_t)slot[i] * 64 + g * 8 + 2 * t) = make_double2(x0, x1);
+              if (slot[i] >= P.n_tiles && g == 0) { sx[8 * J + 2 * t] = x0; sx[8 * J + 2 * t + 1] = x1; }
+            }
+          }
+        }
+      }
+      __syncthreads();     // column J of L (and y_J) visible to everybody
+    }
+
+    // ---- backward substitution  L^T u = y,  columns right to left
+    for (int J = P.ntc - 1; J >= 0; --J) {
+      const int cp0 = P.col_ptr[J], cp1 = P.col_ptr[J + 1];
+      double s0 = 0.0, s1 = 0.0;
+      for (int p = cp0 + 1 + warp; p < cp1; p += kSolveWarps) {
+        const double2 l = *reinterpret_cast<const double2*>(L + (int64_t)p * 64 + g * 8 + 2 * t);
+        const double xv = sx[8 * P.row_idx[p] + g];
+        s0 += l.x * xv;
+        s1 += l.y * xv;
+      }
+#pragma unroll
+      for (int o = 4; o < 32; o <<= 1) {
+        s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      }
+      if (g == 0) { sred[warp * 8 + 2 * t] = s0; sred[warp * 8 + 2 * t + 1] = s1; }
+      __syncthreads();
+      if (warp == 0) {
+        const int cidx = lane & 7;
+        double v = sx[8 * J + cidx];
+#pragma unroll
+        for (int w = 0; w < kSolveWarps; ++w) v -= sred[w * 8 + cidx];
+        // u_c = sum_k W[k][c] v_k
+        double acc = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc += Winv[(int64_t)J * 64 + k * 8 + cidx] * __shfl_sync(0xffffffffu, v, k);
+        if (lane < 8) sx[8 * J + cidx] = acc;
+      }
+      __syncthreads();
+    }
+    for (int i = threadIdx.x; i < P.n_red; i += kSolveThreads) u[mu * P.n_red + i] = sx[i];
+    if (threadIdx.x == 0 && info) info[mu] = s_info;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+//  estimator
+// ------------------------------------------------------------------------------------------------------
+constexpr int kEstThreads = 256;
+constexpr int kEstWarps = kEstThreads / 32;
+constexpr int kTMU = 32;         // parameters per CTA
+constexpr int kLDX = 36;         // shared row stride (doubles): 36 mod 16 == 4 -> conflict-free DMMA fragment loads
+
+struct DevTerm {
+  const double* M;
+  int32_t rows, cols, left_kind, right_kind, qa, qb, out_kind, pad;
+  double coef;
+};
+
+struct EstParams {
+  int32_t n_sub, n_red, Q, n_theta, dmax_pad, qdmax_pad;
+  const int32_t* offsets;     // n_sub + 1
+  const int32_t* nbh_ptr;
+  const int32_t* nbh_idx;
+  const int32_t* term_ptr;    // n_sub + 1
+  const DevTerm* terms;
+  const double* rf2;
+  const double* r_scale;
+};
+
+__global__ void __launch_bounds__(kEstThreads)
+estimate_kernel(EstParams P, int64_t n_mu, const double* __restrict__ theta, const double* __restrict__ u,
+                double* __restrict__ parts) {
+  extern __shared__ double smem[];
+  double* XN = smem;                                   // dmax_pad x kLDX
+  double* XR = XN + (int64_t)P.dmax_pad * kLDX;        // qdmax_pad x kLDX
+  double* TH = XR + (int64_t)P.qdmax_pad * kLDX;       // Q x kTMU
+  double* OUTW = TH + P.Q * kTMU;                      // kEstWarps x 3 x kTMU
+
+  const int sub = blockIdx.y;
+  const int64_t mu0 = (int64_t)blockIdx.x * kTMU;
+  const int nmu = (int)min((int64_t)kTMU, n_mu - mu0);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+
+  // ---- stage theta, u over the neighbourhood (dof-major in shared memory), and U_r = [theta_q u_k]
+  for (int i = threadIdx.x; i < P.Q * kTMU; i += kEstThreads) {
+    const int q = i / kTMU, m = i - q * kTMU;
+    TH[i] = (m < nmu) ? theta[(mu0 + m) * P.n_theta + q] : 0.0;
+  }
+  for (int i = threadIdx.x; i < kEstWarps * 3 * kTMU; i += kEstThreads) OUTW[i] = 0.0;
+  const int nb0 = P.nbh_ptr[sub], nb1 = P.nbh_ptr[sub + 1];
+  int d = 0, lo_self = 0;
+  for (int e = nb0; e < nb1; ++e) {
+    const int k = P.nbh_idx[e];
+    const int off = P.offsets[k], Nk = P.offsets[k + 1] - off;
+    if (k == sub) lo_self = d;
+    for (int i = threadIdx.x; i < Nk * kTMU; i += kEstThreads) {
+      const int m = i / Nk, a = i - m * Nk;
+      XN[(d + a) * kLDX + m] = (m < nmu) ? u[(mu0 + m) * P.n_red + off + a] : 0.0;
+    }
+    d += Nk;
+  }
+  const int dpad = (d + 3) & ~3;
+  for (int i = threadIdx.x; i < (dpad - d) * kTMU; i += kEstThreads) XN[(d + i / kTMU) * kLDX + (i % kTMU)] = 0.0;
+  __syncthreads();
+  {
+    int lo = 0;
+    for (int e = nb0; e < nb1; ++e) {
+      const int k = P.nbh_idx[e];
+      const int Nk = P.offsets[k + 1] - P.offsets[k];
+      for (int i = threadIdx.x; i < P.Q * Nk * kTMU; i += kEstThreads) {
+        const int m = i % kTMU, qa = i / kTMU;      // qa = q * Nk + a
+        const int q = qa / Nk, a = qa - q * Nk;
+        XR[(P.Q * lo + qa) * kLDX + m] = TH[q * kTMU + m] * XN[(lo + a) * kLDX + m];
+      }
+      lo += Nk;
+    }
+    const int qd = P.Q * d, qdpad = (qd + 3) & ~3;
+    for (int i = threadIdx.x; i < (qdpad - qd) * kTMU; i += kEstThreads) XR[(qd + i / kTMU) * kLDX + (i % kTMU)] = 0.0;
+  }
+  __syncthreads();
+
+  // ---- terms
+  for (int ti = P.term_ptr[sub]; ti < P.term_ptr[sub + 1]; ++ti) {
+    const DevTerm T = P.terms[ti];
+    const double* XRt = (T.right_kind == LRBMS_VEC_UR) ? XR : (T.right_kind == LRBMS_VEC_UN ? XN : XN + lo_self * kLDX);
+    const double* XLt = (T.left_kind == LRBMS_VEC_UR) ? XR : (T.left_kind == LRBMS_VEC_UN ? XN : XN + lo_self * kLDX);
+    const int kend = (T.cols + 3) & ~3;
+    double ps[kTMU / 8][2];
+#pragma unroll
+    for (int n = 0; n < kTMU / 8; ++n) ps[n][0] = ps[n][1] = 0.0;
+    for (int r0 = 8 * warp; r0 < T.rows; r0 += 8 * kEstWarps) {
+      double acc[kTMU / 8][2];
+#pragma unroll
+      for (int n = 0; n < kTMU / 8; ++n) acc[n][0] = acc[n][1] = 0.0;
+      const bool rok = r0 + g < T.rows;
+      const double* __restrict__ Mr = T.M + (int64_t)(r0 + g) * T.cols;
+      for (int k0 = 0; k0 < kend; k0 += 4) {
+        const double a = (rok && k0 + t < T.cols) ? __ldg(Mr + k0 + t) : 0.0;
+        const double* xb = XRt + (k0 + t) * kLDX + g;
+#pragma unroll
+        for (int n = 0; n < kTMU / 8; ++n) dmma884(acc[n][0], acc[n][1], a, xb[8 * n]);
+      }
+      // column dot with the left vector: rows r0 + g, parameters 8n + 2t, 8n + 2t + 1
+#pragma unroll
+      for (int n = 0; n < kTMU / 8; ++n) {
+        double l0 = 0.0, l1 = 0.0;
+        if (rok) {
+          if (T.left_kind == LRBMS_VEC_ONE) { l0 = 1.0; l1 = 1.0; }
+          else { l0 = XLt[(r0 + g) * kLDX + 8 * n + 2 * t]; l1 = XLt[(r0 + g) * kLDX + 8 * n + 2 * t + 1]; }
+        }
+        ps[n][0] += l0 * acc[n][0];
+        ps[n][1] += l1 * acc[n][1];
+      }
+    }
+    // reduce over the 8 rows of the tile (lanes with equal t), scale, accumulate in this warp's private slice
+#pragma unroll
+    for (int n = 0; n < kTMU / 8; ++n)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        double v = ps[n][j];
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        v += __shfl_xor_sync(0xffffffffu, v, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 16);
+        if (g == 0) {
+          const int m = 8 * n + 2 * t + j;
+          double cf = T.coef;
+          if (T.qa >= 0) cf *= TH[T.qa * kTMU + m];
+          if (T.qb >= 0) cf *= TH[T.qb * kTMU + m];
+          OUTW[(warp * 3 + T.out_kind) * kTMU + m] += cf * v;
+        }
+      }
+    __syncwarp();
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 3 * kTMU; i += kEstThreads) {
+    const int kind = i / kTMU, m = i - kind * kTMU;
+    if (m >= nmu) continue;
+    double v = 0.0;
+    for (int w = 0; w < kEstWarps; ++w) v += OUTW[(w * 3 + kind) * kTMU + m];
+    if (kind == LRBMS_OUT_R) v = (P.rf2[sub] + v) * P.r_scale[sub];
+    parts[((int64_t)kind * P.n_sub + sub) * n_mu + mu0 + m] = v;
+  }
+}
+
+struct CombineParams {
+  int32_t n_sub, Q, n_theta, alpha_first;
+  double theta_bar[16], theta_hat[16];
+};
+
+// eta = ( sqrt(gamma) ||nc||_2 + ||r + df||_2 / sqrt(alpha_hat) ) / sqrt(alpha_bar)       (estimators.py:99-102),
+// norms over subdomains per parameter column; optional indicators (estimators.py:104-109)
+__global__ void combine_kernel(CombineParams P, int64_t n_mu, const double* __restrict__ theta,
+                               const double* __restrict__ parts, double* __restrict__ eta, double* __restrict__ indicators) {
+  const int64_t mu = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (mu >= n_mu) return;
+  double a_bar = INFINITY, a_hat = INFINITY, g_bar = -INFINITY;
+  for (int q = 0; q < P.Q; ++q) {
+    const double th = theta[mu * P.n_theta + q];
+    const double rb = th / P.theta_bar[q], rh = th / P.theta_hat[q];
+    if (!(P.alpha_first && q > 0)) { a_bar = fmin(a_bar, rb); a_hat = fmin(a_hat, rh); }
+    g_bar = fmax(g_bar, rb);
+  }
+  double snc = 0.0, srd = 0.0;
+  const double* nc = parts;
+  const double* r = parts + (int64_t)P.n_sub * n_mu;
+  const double* df = parts + 2 * (int64_t)P.n_sub * n_mu;
+  for (int i = 0; i < P.n_sub; ++i) {
+    const double a = nc[i * n_mu + mu], b = r[i * n_mu + mu] + df[i * n_mu + mu];
+    snc += a * a;
+    srd += b * b;
+    if (indicators) indicators[i * n_mu + mu] = (2.0 / a_bar) * (g_bar * a * a + (1.0 / a_hat) * b * b);
+  }
+  eta[mu] = (sqrt(g_bar) * sqrt(snc) + sqrt(srd) / sqrt(a_hat)) / sqrt(a_bar);
+}
+
+__global__ void eta_max_kernel(int64_t n, const double* __restrict__ eta, double* __restrict__ max_out,
+                               int64_t* __restrict__ arg_out) {
+  __shared__ double sv[1024];
+  __shared__ int64_t si[1024];
+  double best = -INFINITY;
+  int64_t bi = -1;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const double v = eta[i];
+    if (v > best || bi < 0) { best = v; bi = i; }
+  }
+  sv[threadIdx.x] = best;
+  si[threadIdx.x] = bi;
+  __syncthreads();
+  for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+    if (threadIdx.x < s) {
+      const double v = sv[threadIdx.x + s];
+      const int64_t j = si[threadIdx.x + s];
+      if (j >= 0 && (si[threadIdx.x] < 0 || v > sv[threadIdx.x] || (v == sv[threadIdx.x] && j < si[threadIdx.x]))) {
+        sv[threadIdx.x] = v;
+        si[threadIdx.x] = j;
+      }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { *max_out = sv[0]; *arg_out = si[0]; }
+}
+
+// ------------------------------------------------------------------------------------------------------
+//  plan
+// ------------------------------------------------------------------------------------------------------
+struct OnlinePlan : lrbms_plan {
+  lrbms_symbolic sym;
+  SolveParams sp;
+  EstParams ep;
+  CombineParams cp;
+  int solve_grid = 0;
+  size_t solve_smem = 0, est_smem = 0;
+  bool has_estimator = false;
+  int run(void*) override { return lrbms_fail(ctx, LRBMS_ERR_INVALID, "online plans are run with lrbms_online_*"); }
+};
+
+}  // namespace
+
+extern "C" {
+
+int lrbms_online_plan_create(lrbms_handle_t h, const lrbms_reduced_system_t* sys, lrbms_plan_t* out) {
+  LRBMS_REQUIRE(h, h && sys && out, "online_plan_create: null argument");
+  LRBMS_REQUIRE(h, sys->Q >= 1 && sys->Q <= 16 && sys->Qf >= 1 && sys->Qf <= 16, "online_plan_create: 1 <= Q, Qf <= 16");
+  LRBMS_REQUIRE(h, sys->lhs_blocks && sys->rhs && sys->block_offset && sys->basis_sizes, "online_plan_create: null data pointer");
+  LRBMS_CUDA_CHECK(h, cudaSetDevice(h->device));
+  OnlinePlan* P = new OnlinePlan();
+  P->ctx = h;
+  P->kind = PLAN_ONLINE;
+  std::string err;
+  int rc = lrbms_symbolic_build(P->sym, sys->n_sub, sys->basis_sizes, sys->n_blocks, sys->block_i, sys->block_j, &err);
+  if (rc) { delete P; return lrbms_fail(h, rc, err); }
+  const lrbms_symbolic& S = P->sym;
+  const int Q = sys->Q, Qf = sys->Qf;
+
+  // ---- operator tiles: download the reduced blocks, scatter the lower triangle into 8x8 tiles
+  int64_t n_doubles = 0;
+  for (int q = 0; q < Q; ++q)
+    for (int b = 0; b < sys->n_blocks; ++b)
+      n_doubles = std::max<int64_t>(n_doubles, sys->block_offset[(int64_t)q * sys->n_blocks + b] +
+                                                   (int64_t)S.sizes[sys->block_i[b]] * S.sizes[sys->block_j[b]]);
+  std::vector<double> hb((size_t)std::max<int64_t>(1, n_doubles));
+  if (n_doubles) {
+    cudaError_t e = cudaMemcpy(hb.data(), sys->lhs_blocks, sizeof(double) * n_doubles, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) { delete P; return lrbms_fail(h, LRBMS_ERR_CUDA, cudaGetErrorString(e)); }
+  }
+  std::vector<double> tiles((size_t)Q * S.n_a_tiles * 64, 0.0);
+  auto slot_of = [&](int I, int J) {
+    const int32_t* b = S.row_idx.data() + S.col_ptr[J];
+    const int32_t* e = S.row_idx.data() + S.col_ptr[J + 1];
+    return (int32_t)(std::lower_bound(b, e, I) - S.row_idx.data());
+  };
+  for (int q = 0; q < Q; ++q)
+    for (int b = 0; b < sys->n_blocks; ++b) {
+      const int i = sys->block_i[b], j = sys->block_j[b];
+      if (i < j) continue;
+      const double* blk = hb.data() + sys->block_offset[(int64_t)q * sys->n_blocks + b];
+      const int Ni = S.sizes[i], Nj = S.sizes[j];
+      for (int a = 0; a < Ni; ++a)
+        for (int c = 0; c < Nj; ++c) {
+          const int r = S.offsets[i] + a, cc = S.offsets[j] + c;
+          if (r < cc) continue;
+          const int ai = S.a_map[slot_of(r / 8, cc / 8)];
+          double* tl = tiles.data() + ((size_t)q * S.n_a_tiles + ai) * 64;
+          tl[(r & 7) * 8 + (cc & 7)] = blk[(int64_t)a * Nj + c];
+          if (r / 8 == cc / 8) tl[(cc & 7) * 8 + (r & 7)] = blk[(int64_t)a * Nj + c];
+        }
+    }
+  std::vector<double> rhs_h((size_t)Qf * S.n_pad, 0.0);
+  {
+    std::vector<double> tmp((size_t)Qf * S.n_red);
+    cudaError_t e = cudaMemcpy(tmp.data(), sys->rhs, sizeof(double) * tmp.size(), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) { delete P; return lrbms_fail(h, LRBMS_ERR_CUDA, cudaGetErrorString(e)); }
+    for (int q = 0; q < Qf; ++q) std::copy(tmp.begin() + (size_t)q * S.n_red, tmp.begin() + (size_t)(q + 1) * S.n_red, rhs_h.begin() + (size_t)q * S.n_pad);
+  }
+
+  SolveParams& sp = P->sp;
+  sp.n_red = S.n_red; sp.n_pad = S.n_pad; sp.ntc = S.ntc; sp.n_tiles = (int32_t)S.n_tiles(); sp.Q = Q; sp.Qf = Qf;
+  sp.n_theta = Q + Qf; sp.n_a_tiles = S.n_a_tiles;
+  sp.work_stride = ((int64_t)S.n_tiles() + 2 * S.ntc) * 64;
+  int32_t *d_i32 = nullptr;
+  double* d_f64 = nullptr;
+#define UP_I32(field, vec) do { rc = plan_upload(P, &d_i32, vec); if (rc) { lrbms_plan_destroy(P); return rc; } field = d_i32; } while (0)
+#define UP_F64(field, vec) do { rc = plan_upload(P, &d_f64, vec); if (rc) { lrbms_plan_destroy(P); return rc; } field = d_f64; } while (0)
+  UP_I32(sp.col_ptr, S.col_ptr);
+  UP_I32(sp.row_idx, S.row_idx);
+  UP_I32(sp.pair_ptr, S.pair_ptr);
+  UP_I32(sp.pair_a, S.pair_a);
+  UP_I32(sp.pair_b, S.pair_b);
+  UP_I32(sp.a_map, S.a_map);
+  UP_F64(sp.a_tiles, tiles);
+  UP_F64(sp.rhs, rhs_h);
+
+  P->solve_smem = sizeof(double) * ((size_t)S.n_pad + 64 + 64 + kSolveWarps * 8 + sp.n_theta);
+  if (P->solve_smem > (size_t)h->max_smem_optin) {
+    lrbms_plan_destroy(P);
+    return lrbms_fail(h, LRBMS_ERR_UNSUPPORTED, "online_plan_create: reduced dimension too large for the shared-memory solve vector");
+  }
+  if (P->solve_smem > 48 * 1024)
+    LRBMS_CUDA_CHECK(h, cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->solve_smem));
+  {
+    int per_sm = 0;
+    LRBMS_CUDA_CHECK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, solve_kernel, kSolveThreads, P->solve_smem));
+    if (per_sm < 1) per_sm = 1;
+    const char* env = getenv("LRBMS_SOLVE_CTAS_PER_SM");
+    if (env && atoi(env) > 0) per_sm = std::min(per_sm, atoi(env));
+    P->solve_grid = per_sm * h->sm_count;
+  }
+
+  // ---- estimator tables
+  P->has_estimator = sys->n_terms > 0;
+  if (P->has_estimator) {
+    LRBMS_REQUIRE(h, sys->nbh_ptr && sys->nbh_idx && sys->terms && sys->est_matrices && sys->rf_squared && sys->r_scale &&
+                         sys->theta_bar && sys->theta_hat, "online_plan_create: estimator data missing");
+    EstParams& ep = P->ep;
+    ep.n_sub = S.n_sub; ep.n_red = S.n_red; ep.Q = Q; ep.n_theta = Q + Qf;
+    std::vector<int32_t> nbh_ptr(sys->nbh_ptr, sys->nbh_ptr + S.n_sub + 1);
+    std::vector<int32_t> nbh_idx(sys->nbh_idx, sys->nbh_idx + nbh_ptr[S.n_sub]);
+    int dmax = 0;
+    std::vector<int> dsub(S.n_sub, 0);
+    for (int i = 0; i < S.n_sub; ++i) {
+      int d = 0;
+      bool self = false;
+      for (int e = nbh_ptr[i]; e < nbh_ptr[i + 1]; ++e) {
+        const int k = nbh_idx[e];
+        if (k < 0 || k >= S.n_sub) { lrbms_plan_destroy(P); return lrbms_fail(h, LRBMS_ERR_INVALID, "online_plan_create: neighbourhood index out of range"); }
+        d += S.sizes[k];
+        self |= (k == i);
+      }
+      if (!self) { lrbms_plan_destroy(P); return lrbms_fail(h, LRBMS_ERR_INVALID, "online_plan_create: neighbourhood must contain the subdomain itself"); }
+      dsub[i] = d;
+      dmax = std::max(dmax, d);
+    }
+    ep.dmax_pad = (dmax + 3) & ~3;
+    ep.qdmax_pad = (Q * dmax + 3) & ~3;
+    // sort terms by subdomain, validate shapes
+    std::vector<std::vector<DevTerm>> per_sub(S.n_sub);
+    for (int k = 0; k < sys->n_terms; ++k) {
+      const lrbms_estimator_term_t& T = sys->terms[k];
+      bool ok = T.subdomain >= 0 && T.subdomain < S.n_sub && T.out_kind >= 0 && T.out_kind < 3 && T.qa < Q && T.qb < Q;
+      auto dim_of = [&](int kind, int i) { return kind == LRBMS_VEC_ONE ? 1 : kind == LRBMS_VEC_UI ? S.sizes[i] : kind == LRBMS_VEC_UN ? dsub[i] : Q * dsub[i]; };
+      if (ok) ok = T.rows == dim_of(T.left_kind, T.subdomain) && T.cols == dim_of(T.right_kind, T.subdomain) && T.right_kind != LRBMS_VEC_ONE;
+      if (!ok) { lrbms_plan_destroy(P); return lrbms_fail(h, LRBMS_ERR_INVALID, "online_plan_create: estimator term " + std::to_string(k) + " is inconsistent"); }
+      DevTerm D;
+      D.M = sys->est_matrices + T.matrix_offset; D.rows = T.rows; D.cols = T.cols; D.left_kind = T.left_kind;
+      D.right_kind = T.right_kind; D.qa = T.qa; D.qb = T.qb; D.out_kind = T.out_kind; D.pad = 0; D.coef = T.coef;
+      per_sub[T.subdomain].push_back(D);
+    }
+    std::vector<int32_t> term_ptr(S.n_sub + 1, 0);
+    std::vector<DevTerm> terms;
+    double est_flops = 0;
+    for (int i = 0; i < S.n_sub; ++i) {
+      for (const DevTerm& D : per_sub[i]) { terms.push_back(D); est_flops += 2.0 * D.rows * D.cols; }
+      term_ptr[i + 1] = (int32_t)terms.size();
+    }
+    P->info_flops = est_flops;   // estimator flops per mu (factor flops are in lrbms_symbolic_info)
+    UP_I32(ep.offsets, S.offsets);
+    UP_I32(ep.nbh_ptr, nbh_ptr);
+    UP_I32(ep.nbh_idx, nbh_idx);
+    UP_I32(ep.term_ptr, term_ptr);
+    DevTerm* d_terms = nullptr;
+    rc = plan_upload(P, &d_terms, terms);
+    if (rc) { lrbms_plan_destroy(P); return rc; }
+    ep.terms = d_terms;
+    std::vector<double> rf2(sys->rf_squared, sys->rf_squared + S.n_sub), rs(sys->r_scale, sys->r_scale + S.n_sub);
+    UP_F64(ep.rf2, rf2);
+    UP_F64(ep.r_scale, rs);
+    P->est_smem = sizeof(double) * ((size_t)(ep.dmax_pad + ep.qdmax_pad) * kLDX + (size_t)Q * kTMU + kEstWarps * 3 * kTMU);
+    if (P->est_smem > (size_t)h->max_smem_optin) {
+      lrbms_plan_destroy(P);
+      return lrbms_fail(h, LRBMS_ERR_UNSUPPORTED, "online_plan_create: neighbourhood too large for the estimator kernel's shared memory");
+    }
+    if (P->est_smem > 48 * 1024)
+      LRBMS_CUDA_CHECK(h, cudaFuncSetAttribute(estimate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->est_smem));
+    CombineParams& cp = P->cp;
+    cp.n_sub = S.n_sub; cp.Q = Q; cp.n_theta = Q + Qf; cp.alpha_first = sys->alpha_returns_first;
+    for (int q = 0; q < Q; ++q) { cp.theta_bar[q] = sys->theta_bar[q]; cp.theta_hat[q] = sys->theta_hat[q]; }
+  }
+#undef UP_I32
+#undef UP_F64
+  P->info_launches = 3;
+  P->info_ctas = P->solve_grid;
+  *out = P;
+  return LRBMS_OK;
+}
+
+static size_t solve_ws_bytes(const OnlinePlan* P, int64_t n_mu) {
+  const int64_t ctas = std::min<int64_t>(P->solve_grid, std::max<int64_t>(1, n_mu));
+  return (size_t)ctas * P->sp.work_stride * sizeof(double);
+}
+static size_t parts_ws_bytes(const OnlinePlan* P, int64_t n_mu) {
+  return (size_t)3 * P->sym.n_sub * std::max<int64_t>(1, n_mu) * sizeof(double);
+}
+
+int lrbms_online_workspace_bytes(lrbms_plan_t plan, int64_t n_mu, size_t* bytes) {
+  if (!plan || plan->kind != PLAN_ONLINE || !bytes) return LRBMS_ERR_INVALID;
+  const OnlinePlan* P = static_cast<const OnlinePlan*>(plan);
+  *bytes = ((solve_ws_bytes(P, n_mu) + 255) & ~(size_t)255) + parts_ws_bytes(P, n_mu);
+  return LRBMS_OK;
+}
+
+int lrbms_online_solve(lrbms_plan_t plan, int64_t n_mu, const double* theta, double* u, int32_t* info, void* workspace,
+                       size_t workspace_bytes, void* stream) {
+  if (!plan || plan->kind != PLAN_ONLINE) return LRBMS_ERR_INVALID;
+  OnlinePlan* P = static_cast<OnlinePlan*>(plan);
+  LRBMS_REQUIRE(P->ctx, theta && u && workspace, "online_solve: null argument");
+  if (n_mu <= 0) return LRBMS_OK;
+  LRBMS_REQUIRE(P->ctx, workspace_bytes >= solve_ws_bytes(P, n_mu), "online_solve: workspace too small (see lrbms_online_workspace_bytes)");
+  const int grid = (int)std::min<int64_t>(P->solve_grid, n_mu);
+  solve_kernel<<<grid, kSolveThreads, P->solve_smem, (cudaStream_t)stream>>>(P->sp, n_mu, theta, u, info, (double*)workspace);
+  LRBMS_CUDA_CHECK(P->ctx, cudaGetLastError());
+  return LRBMS_OK;
+}
+
+int lrbms_online_estimate(lrbms_plan_t plan, int64_t n_mu, const double* theta, const double* u, double* eta, double* parts,
+                          double* indicators, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!plan || plan->kind != PLAN_ONLINE) return LRBMS_ERR_INVALID;
+  OnlinePlan* P = static_cast<OnlinePlan*>(plan);
+  LRBMS_REQUIRE(P->ctx, P->has_estimator, "online_estimate: the plan was created without estimator terms");
+  LRBMS_REQUIRE(P->ctx, theta && u && eta, "online_estimate: null argument");
+  if (n_mu <= 0) return LRBMS_OK;
+  double* pbuf = parts;
+  if (!pbuf) {
+    const size_t off = (solve_ws_bytes(P, n_mu) + 255) & ~(size_t)255;
+    LRBMS_REQUIRE(P->ctx, workspace && workspace_bytes >= off + parts_ws_bytes(P, n_mu), "online_estimate: workspace too small");
+    pbuf = reinterpret_cast<double*>(reinterpret_cast<char*>(workspace) + off);
+  }
+  dim3 grid((unsigned)((n_mu + kTMU - 1) / kTMU), (unsigned)P->sym.n_sub);
+  estimate_kernel<<<grid, kEstThreads, P->est_smem, (cudaStream_t)stream>>>(P->ep, n_mu, theta, u, pbuf);
+  combine_kernel<<<(unsigned)((n_mu + 127) / 128), 128, 0, (cudaStream_t)stream>>>(P->cp, n_mu, theta, pbuf, eta, indicators);
+  LRBMS_CUDA_CHECK(P->ctx, cudaGetLastError());
+  return LRBMS_OK;
+}
+
+int lrbms_online_sweep(lrbms_plan_t plan, int64_t n_mu, const double* theta, double* u, double* eta, double* parts,
+                       double* indicators, int32_t* info, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = lrbms_online_solve(plan, n_mu, theta, u, info, workspace, workspace_bytes, stream);
+  if (rc) return rc;
+  return lrbms_online_estimate(plan, n_mu, theta, u, eta, parts, indicators, workspace, workspace_bytes, stream);
+}
+
+int lrbms_eta_max(lrbms_handle_t h, int64_t n_mu, const double* eta, double* max_out, int64_t* argmax_out, void* stream) {
+  LRBMS_REQUIRE(h, h && eta && max_out && argmax_out && n_mu > 0, "eta_max: bad argument");
+  eta_max_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(n_mu, eta, max_out, argmax_out);
+  LRBMS_CUDA_CHECK(h, cudaGetLastError());
+  return LRBMS_OK;
+}
+
+}  // extern "C"
