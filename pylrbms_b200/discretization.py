@@ -1,0 +1,167 @@
+"""The block-SWIPDG discretization object the LRBMS hot path consumes, resident in HBM.
+
+``discretize(data)`` restates the assembly-independent part of the reference's ``discretize()``
+(``discretize_elliptic_block_swipdg.py:581-811``): it wraps host-assembled CSR blocks
+(:class:`pylrbms_b200.swipdg_fixture.BlockSwipdgData`, standing in for dune-gdt assembly, which is out of scope)
+into the same operator dictionary -- same names, same source / range spaces, same compositions -- with every
+matrix uploaded to the device once.  Matrices that appear in several operators share one upload.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .estimators import EllipticEstimator
+from .kernels import DeviceCsr
+from .operators import (BlockDiagonalOperator, BlockOperator, BlockProjectionOperator, BlockRowOperator, Concatenation,
+                        CsrOperator, FluxReconstructionOperator, LincombOperator, OswaldInterpolationErrorOperator,
+                        VectorFunctional)
+from .parameters import ExpressionParameterFunctional, ProductParameterFunctional, as_functional, parse_parameter
+from .vectorarray import BlockVectorSpace, GpuVectorSpace
+
+
+class BlockSwipdgDiscretization:
+    """``DuneDiscretization`` stand-in (reference ``discretize...:203-225``): ``operator``, ``rhs``, ``operators``,
+    ``products``, ``estimator``, ``solution_space``, ``neighborhoods``, ``shape_functions``."""
+
+    def __init__(self, operator, rhs, products=None, operators=None, estimator=None, parameter_type=None,
+                 neighborhoods=None, shape_function_data=None, solution_space=None, parameter_range=None, name=None):
+        self.operator, self.rhs = operator, rhs
+        self.products = dict(products or {})
+        self.operators = dict(operators or {})
+        self.operators.setdefault('operator', operator)
+        self.operators.setdefault('rhs', rhs)
+        self.estimator = estimator
+        self.parameter_type = dict(parameter_type or {})
+        self.parameter_range = parameter_range
+        self.neighborhoods = neighborhoods
+        self._shape_function_data = shape_function_data
+        self.solution_space = solution_space if solution_space is not None else operator.source
+        self.name = name
+        self.linear = True
+
+    def with_(self, **kw):
+        import copy
+        new = copy.copy(self)
+        for k, v in kw.items():
+            setattr(new, k, v)
+        if 'operators' in kw:
+            new.operator = kw['operators'].get('operator', new.operator)
+            new.rhs = kw['operators'].get('rhs', new.rhs)
+        return new
+
+    def parse_parameter(self, mu):
+        return parse_parameter(mu, self.parameter_type)
+
+    def solve(self, mu=None):
+        raise NotImplementedError('the fine-scale (FOM) solve runs in dune-gdt / ISTL in the reference and is outside '
+                                  'the LRBMS hot path (SURVEY.md section 2.1 #3); solve the reduced model instead')
+
+    def estimate(self, U, mu=None, decompose=False):
+        """Estimate for a *fine-scale* block array ``U`` through the generic operator chain, one parameter at a time,
+        exactly as the reference does (``estimators.py:45-112``)."""
+        return self.estimator.estimate(U, self.parse_parameter(mu), self, decompose=decompose)
+
+    def shape_functions(self, subdomain, order=0):
+        """reference ``discretize...:187-200``: constant 1, then x, y, x*y."""
+        sf = self._shape_function_data[subdomain]
+        return self.solution_space.subspaces[subdomain].from_data(sf[:(1 if order == 0 else 4)])
+
+
+def discretize(data, alpha_returns_first=True):
+    """Build the device-resident operator set of SURVEY.md Appendix B from host CSR data.
+
+    Returns ``(d, data_dict)`` like the reference's ``discretize()`` (``discretize...:811``)."""
+    S, Q = data.num_subdomains, data.Q
+    lambda_coeffs = [as_functional(c, data.parameter_type) for c in data.coefficients]
+    dom = [GpuVectorSpace(int(data.n[i]), 'domain_{}'.format(i)) for i in range(S)]
+
+    # ---- block lhs (discretize...:475-507, 586)
+    block_ops = []
+    for q in range(Q):
+        ops = np.full((S, S), None, dtype=object)
+        for (i, j), M in data.lhs[q].items():
+            ops[i, j] = CsrOperator(M, source_id=dom[j].id, range_id=dom[i].id, name='local_block_{}-{}'.format(i, j))
+        block_ops.append(BlockOperator(ops, range_spaces=dom, source_spaces=dom, name='BlockOp'))
+    block_op = LincombOperator(block_ops, lambda_coeffs, name='lhs')
+    solution_space = block_op.source
+    # ---- block rhs (discretize...:523-527, 598)
+    rhs_blocks = [dom[i].from_data(data.rhs[i]) for i in range(S)]
+    block_rhs = LincombOperator([VectorFunctional(solution_space.make_array(rhs_blocks))], [1.], name='rhs')
+
+    # ---- Oswald interpolation error / flux reconstruction (discretize...:606-618)
+    oi_op = BlockDiagonalOperator(
+        [OswaldInterpolationErrorOperator(i, solution_space, data.neighborhoods[i],
+                                          [data.oi[(i, k)] for k in data.neighborhoods[i]]) for i in range(S)],
+        name='oswald_interpolation_error')
+    fr_op = LincombOperator(
+        [BlockDiagonalOperator([FluxReconstructionOperator(i, solution_space, data.neighborhoods[i], data.m,
+                                                           [data.fr[q][(i, k)] for k in data.neighborhoods[i]])
+                                for i in range(S)]) for q in range(Q)],
+        lambda_coeffs, name='flux_reconstruction')
+
+    operators, local_l2_products = {}, []
+    for ii in range(S):
+        neighborhood = data.neighborhoods[ii]
+        did, rid = 'domain_{}'.format(ii), 'LOCALRT_{}'.format(ii)
+        # local products (discretize...:644-691)
+        name = 'local_energy_dg_product_{}'.format(ii)
+        operators[name] = CsrOperator(data.energy[ii], source_id=did, range_id=did, name=name)
+        local_l2_product = CsrOperator(data.l2[ii], source_id=did, range_id=did, name='local_l2_product_{}'.format(ii))
+        local_l2_products.append(local_l2_product)
+        local_elliptic_product = CsrOperator(data.elliptic[ii], source_id=did, range_id=did)
+        # projections (discretize...:695-717)
+        local_projection = BlockProjectionOperator(solution_space, ii)
+        ops = [None] * S
+        for kk in neighborhood:
+            component = data.neighborhoods[kk].index(ii)
+            assert fr_op.range.subspaces[kk].subspaces[component].id == rid
+            ops[kk] = BlockProjectionOperator(fr_op.range.subspaces[kk], component)
+        local_rt_projection = BlockRowOperator(ops, source_spaces=fr_op.range.subspaces,
+                                               name='local_rt_projection_{}'.format(ii))
+        ops = [None] * S
+        for kk in neighborhood:
+            component = data.neighborhoods[kk].index(ii)
+            assert oi_op.range.subspaces[kk].subspaces[component].id == did
+            ops[kk] = BlockProjectionOperator(oi_op.range.subspaces[kk], component)
+        local_oi_projection = BlockRowOperator(ops, source_spaces=oi_op.range.subspaces,
+                                               name='local_oi_projection_{}'.format(ii))
+        # divergence (discretize...:721-729)
+        local_div_op = CsrOperator(data.div[ii], source_id=rid, range_id=did, name='local_divergence_{}'.format(ii))
+        # nonconformity (discretize...:733-735)
+        operators['nc_{}'.format(ii)] = Concatenation([local_oi_projection.T, local_elliptic_product, local_oi_projection],
+                                                      name='nonconformity_{}'.format(ii))
+        # residual (discretize...:739-748); only built for a single rhs term, like the reference
+        local_div = Concatenation([local_div_op, local_rt_projection])
+        local_rhs = VectorFunctional(block_rhs.operators[0]._array._blocks[ii])
+        operators['r_fd_{}'.format(ii)] = Concatenation([local_rhs, local_div], name='r1_{}'.format(ii))
+        operators['r_dd_{}'.format(ii)] = Concatenation([local_div.T, local_l2_product, local_div], name='r2_{}'.format(ii))
+        # diffusive flux (discretize...:319-378, 752-770)
+        aa_ops = []
+        for q in range(Q):
+            for q2 in range(Q):
+                df_ops = np.full((S, S), None, dtype=object)
+                df_ops[ii, ii] = CsrOperator(data.aa[q][q2][ii], source_id=did, range_id=did)
+                aa_ops.append(BlockOperator(df_ops, range_spaces=dom, source_spaces=dom))
+        operators['df_aa_{}'.format(ii)] = LincombOperator(
+            aa_ops, [ProductParameterFunctional([c1, c2]) for c1 in lambda_coeffs for c2 in lambda_coeffs],
+            name='diffusive_flux_aa_{}'.format(ii))
+        bbm = CsrOperator(data.bb[ii], source_id=rid, range_id=rid)
+        operators['df_bb_{}'.format(ii)] = Concatenation([local_rt_projection.T, bbm, local_rt_projection],
+                                                         name='diffusive_flux_bb_{}'.format(ii))
+        operators['df_ab_{}'.format(ii)] = LincombOperator(
+            [Concatenation([local_projection.T, CsrOperator(data.ab[q][ii], source_id=rid, range_id=did),
+                            local_rt_projection]) for q in range(Q)],
+            lambda_coeffs, name='diffusive_flux_ab_{}'.format(ii))
+
+    estimator = EllipticEstimator(list(range(S)), data.min_diffusion_evs, data.subdomain_diameters,
+                                  data.local_eta_rf_squared, lambda_coeffs, data.mu_bar, data.mu_hat, fr_op, oi_op,
+                                  alpha_returns_first=alpha_returns_first)
+    l2_product = BlockDiagonalOperator(local_l2_products, name='l2')
+    d = BlockSwipdgDiscretization(block_op, block_rhs, products={'l2': l2_product}, operators=operators,
+                                  estimator=estimator, parameter_type=data.parameter_type,
+                                  neighborhoods=data.neighborhoods, shape_function_data=data.shape_functions,
+                                  solution_space=solution_space, parameter_range=data.parameter_range,
+                                  name=data.meta.get('problem'))
+    info = {'num_subdomains': S, 'neighborhoods': data.neighborhoods, 'n': data.n, 'm': data.m,
+            'local_products': [operators['local_energy_dg_product_{}'.format(i)] for i in range(S)]}
+    return d, info

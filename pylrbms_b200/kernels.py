@@ -1,0 +1,97 @@
+"""Thin host helpers over the C ABI: device CSR storage, descriptor builders, one-shot SpMM / projection calls.
+
+Everything numerical happens inside ``liblrbms_sm100`` (``include/lrbms_sm100.h``); this module only packs
+pointers.  One-shot helpers create a plan, run it and drop it -- the reductor batches all of its blocks into a
+single plan instead (:mod:`pylrbms_b200.reductor`).
+"""
+from __future__ import annotations
+
+import numpy as np
+import scipy.sparse as sp
+
+from ._lib import Handle, ProjectDesc, SpmmDesc, make_project_plan, make_spmm_plan
+
+
+def _torch():
+    import torch
+    return torch
+
+
+class DeviceCsr:
+    """CSR matrix resident in HBM: ``rowptr`` / ``colind`` int32, ``values`` float64.
+
+    Replaces ``IstlRowMajorSparseMatrixDouble`` (reference ``discretize_elliptic_block_swipdg.py:10-14``)."""
+
+    def __init__(self, matrix):
+        torch = _torch()
+        M = sp.csr_matrix(matrix)
+        if not M.has_sorted_indices:
+            M = M.copy()
+            M.sort_indices()
+        self.shape = tuple(int(s) for s in M.shape)
+        self.nnz = int(M.nnz)
+        self.rowptr = torch.from_numpy(np.ascontiguousarray(M.indptr, dtype=np.int32)).cuda()
+        self.colind = torch.from_numpy(np.ascontiguousarray(M.indices if M.nnz else np.zeros(1), dtype=np.int32)).cuda()
+        self.values = torch.from_numpy(np.ascontiguousarray(M.data if M.nnz else np.zeros(1), dtype=np.float64)).cuda()
+        self._host = M
+        self._T = None
+
+    @property
+    def host(self):
+        """The host CSR this was uploaded from (kept for the transposed upload and for inspection)."""
+        return self._host
+
+    @property
+    def T(self):
+        if self._T is None:
+            self._T = DeviceCsr(self._host.T.tocsr())
+            self._T._T = self
+        return self._T
+
+    @property
+    def device_bytes(self):
+        return 4 * (self.shape[0] + 1) + 12 * self.nnz
+
+
+def spmm_desc(csr, V_ptr, ldv, N, W_ptr, ldw):
+    return SpmmDesc(csr.rowptr.data_ptr(), csr.colind.data_ptr(), csr.values.data_ptr(), csr.shape[0], csr.shape[1],
+                    V_ptr, ldv, N, W_ptr, ldw)
+
+
+def project_desc(csr, n_rows, VL_ptr, ldl, NL, VR_ptr, ldr, NR, out_ptr, ldo, alpha=1.0):
+    """``csr=None`` selects the identity operator (Gram matrix ``VL^T VR``)."""
+    if csr is None:
+        return ProjectDesc(None, None, None, n_rows, n_rows, VL_ptr, ldl, NL, VR_ptr, ldr, NR, out_ptr, ldo, float(alpha))
+    assert csr.shape[0] == n_rows
+    return ProjectDesc(csr.rowptr.data_ptr(), csr.colind.data_ptr(), csr.values.data_ptr(), csr.shape[0], csr.shape[1],
+                       VL_ptr, ldl, NL, VR_ptr, ldr, NR, out_ptr, ldo, float(alpha))
+
+
+def spmm_once(csr, V, range_space):
+    """``W = A V`` for a :class:`GpuVectorArray` ``V``; returns a new array in ``range_space``."""
+    from .vectorarray import GpuVectorArray
+    W = GpuVectorArray(range_space, None, len(V))
+    if len(V) == 0 or csr.shape[0] == 0:
+        return W
+    h = Handle.get()
+    plan = make_spmm_plan(h, [spmm_desc(csr, V.device_ptr, V.ld, len(V), W.device_ptr, W.ld)], [csr, V, W])
+    plan.run()
+    plan.destroy()
+    return W
+
+
+def project_once(csr, VL, VR, alpha=1.0):
+    """``alpha * VL^T (A VR)`` as a host ``(len(VL), len(VR))`` array (``csr=None``: ``VL^T VR``)."""
+    torch = _torch()
+    NL, NR = len(VL), len(VR)
+    if NL == 0 or NR == 0:
+        return np.zeros((NL, NR))
+    out = torch.zeros((NL, NR), dtype=torch.float64, device='cuda')
+    if VL.dim == 0:
+        return out.cpu().numpy()
+    h = Handle.get()
+    d = project_desc(csr, VL.dim, VL.device_ptr, VL.ld, NL, VR.device_ptr, VR.ld, NR, out.data_ptr(), NR, alpha)
+    plan = make_project_plan(h, [d], [csr, VL, VR, out])
+    plan.run()
+    plan.destroy()
+    return out.cpu().numpy()
