@@ -90,6 +90,42 @@ class VA:
         return not np.any(self.data)
 
 
+class _ZeroVA(VA):
+    """Shared, immutable all-zero array (allocation saver of the oracle; any in-place use is a bug and raises)."""
+
+    def __init__(self, space, count):
+        z = np.zeros((count, space.dim))
+        z.setflags(write=False)
+        super().__init__(z, space)
+
+    def _immutable(self, *a, **k):
+        raise RuntimeError('shared zero array must not be modified in place')
+
+    append = scal = axpy = _immutable
+
+    def copy(self):
+        return VA(np.zeros(self.data.shape), self.space)
+
+    def is_zero(self):
+        return True
+
+
+_ZERO_CACHE = {}
+
+
+def shared_zeros(space, count):
+    """An all-zero array of ``space`` that may be shared between callers (read-only)."""
+    if isinstance(space, BlockSpace):
+        return BlockVA([shared_zeros(s, count) for s in space.subspaces], space)
+    key = (space.dim, space.id, count)
+    z = _ZERO_CACHE.get(key)
+    if z is None:
+        if len(_ZERO_CACHE) > 8192:
+            _ZERO_CACHE.clear()
+        z = _ZERO_CACHE[key] = _ZeroVA(space, count)
+    return z
+
+
 class BlockSpace(Space):
     def __init__(self, subspaces, id_=None):
         self.subspaces = list(subspaces)
@@ -142,12 +178,10 @@ class BlockVA:
             b.append(o)
 
     def scal(self, alpha):
-        for b in self._blocks:
-            b.scal(alpha)
+        self._blocks = [b if isinstance(b, _ZeroVA) else _scaled(b, alpha) for b in self._blocks]
 
     def axpy(self, alpha, x):
-        for b, o in zip(self._blocks, x._blocks):
-            b.axpy(alpha, o)
+        self._blocks = [b if isinstance(o, _ZeroVA) else _axpyed(b, alpha, o) for b, o in zip(self._blocks, x._blocks)]
 
     def dot(self, other):
         return sum(b.dot(o) for b, o in zip(self._blocks, other._blocks))
@@ -169,6 +203,22 @@ class BlockVA:
 
     def is_zero(self):
         return all(b.is_zero() for b in self._blocks)
+
+
+def _scaled(b, alpha):
+    if isinstance(b, BlockVA):
+        new = BlockVA(list(b._blocks), b.space)
+        new.scal(alpha)
+        return new
+    return VA(b.data * alpha, b.space)
+
+
+def _axpyed(b, alpha, o):
+    if isinstance(b, BlockVA):
+        new = BlockVA(list(b._blocks), b.space)
+        new.axpy(alpha, o)
+        return new
+    return VA(b.data + alpha * o.data, b.space)
 
 
 NUMBER_SPACE = Space(1, 'SCALARS')
@@ -407,12 +457,13 @@ class BlockOperator(Operator):
         nr, ns = self._blocks.shape
         rs = self.range.subspaces if self._block_range else [self.range]
         for i in range(nr):
-            acc = rs[i].zeros(len(U))
+            acc = None
             for j in range(ns):
                 b = self._blocks[i, j]
                 if b is not None:
-                    acc.axpy(1.0, b.apply(Ub[j], mu=mu))
-            out.append(acc)
+                    W = b.apply(Ub[j], mu=mu)
+                    acc = W if acc is None else _axpyed(acc, 1.0, W)
+            out.append(acc if acc is not None else shared_zeros(rs[i], len(U)))
         return BlockVA(out, self.range) if self._block_range else out[0]
 
     @property
@@ -450,9 +501,7 @@ class BlockEmbeddingOperator(Operator):
         self.source = block_space.subspaces[index]
 
     def apply(self, U, mu=None):
-        R = self.range.zeros(len(U))
-        R._blocks[self.index] = U.copy()
-        return R
+        return _embed(self.range, self.index, U.copy())
 
     @property
     def T(self):
@@ -513,10 +562,22 @@ def project(op, range_basis, source_basis):
 
 
 def _embed(space, index, basis):
-    """Zero-embed ``basis`` (an array in ``space.subspaces[index]``) into block ``space``."""
-    R = space.zeros(len(basis))
-    R._blocks[index] = basis
-    return R
+    """Zero-embed ``basis`` (an array in ``space.subspaces[index]``) into block ``space``; the zero blocks are shared
+    read-only arrays, which keeps the large configurations affordable."""
+    return BlockVA([basis if k == index else shared_zeros(sub, len(basis)) for k, sub in enumerate(space.subspaces)], space)
+
+
+def _touched_source_blocks(op):
+    """Source subspaces a chain can depend on: those its right-most selection operator reads.  Every other subspace
+    is mapped to exactly zero (and would be dropped by the ``is_zero`` test below), so skipping it changes nothing
+    but the run time."""
+    while isinstance(op, Concatenation):
+        op = op.operators[-1]
+    if isinstance(op, BlockRowOperator):
+        return [j for j, b in enumerate(op._blocks[0, :]) if b is not None]
+    if isinstance(op, BlockProjectionOperator):
+        return [op.index]
+    return None
 
 
 def project_system(op, range_bases, source_bases):
@@ -539,7 +600,10 @@ def project_system(op, range_bases, source_bases):
             if b is not None:
                 blocks[i, j] = project(b, range_bases[rng_sub[i].id], source_bases[src_sub[j].id])
     else:
+        touched = _touched_source_blocks(op) if src_block else None
         for j, ss in enumerate(src_sub):
+            if touched is not None and j not in touched:
+                continue
             SB = source_bases[ss.id]
             W = op.apply(_embed(op.source, j, SB) if src_block else SB)
             if W.is_zero():

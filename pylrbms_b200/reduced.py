@@ -487,6 +487,31 @@ class ReducedModel:
         """``rd.estimate(U, mu=mu, decompose=False)`` (reference ``online_enrichment.py:61,74``)."""
         return self.estimator.estimate(U, self.parse_parameter(mu), self, decompose=decompose)
 
+    def sweep_into(self, mus, u_host, eta_host):
+        """End-to-end batched sweep with caller-provided (ideally pinned) host outputs: host parameters -> coefficient
+        matrix -> H2D -> solve + estimate -> D2H of all reduced solutions ``(n_mu, n_red)`` and ``eta`` ``(n_mu,)``.
+        Returns the number of parameters flagged as not positive definite (0 = all fine)."""
+        torch = _torch()
+        th = self.thetas(mus)
+        n_mu = th.shape[0]
+        bufs = self._work.get('e2e')
+        if bufs is None or bufs[0].shape[0] != n_mu:
+            bufs = (torch.empty(th.shape, dtype=torch.float64).pin_memory(),
+                    torch.empty(th.shape, dtype=torch.float64, device='cuda'),
+                    torch.empty((n_mu, self.n_red), dtype=torch.float64, device='cuda'),
+                    torch.empty(n_mu, dtype=torch.float64, device='cuda'),
+                    torch.empty(n_mu, dtype=torch.int32, device='cuda'))
+            self._work['e2e'] = bufs
+        th_pin, th_dev, u, eta, info = bufs
+        th_pin.copy_(torch.from_numpy(th))
+        th_dev.copy_(th_pin, non_blocking=True)
+        self.sweep_device(th_dev, u, eta, info=info)
+        u_host.copy_(u, non_blocking=True)
+        eta_host.copy_(eta, non_blocking=True)
+        bad = int((info != 0).sum().item())          # synchronises the stream: the copies above are complete
+        torch.cuda.current_stream().synchronize()
+        return bad
+
     def sweep(self, mus, decompose=False):
         """Solve and estimate a parameter batch in one call: ``(U, eta)`` or ``(U, eta, (nc, r, df), indicators)``."""
         torch = _torch()
