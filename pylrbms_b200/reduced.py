@@ -512,6 +512,22 @@ class ReducedModel:
         torch.cuda.current_stream().synchronize()
         return bad
 
+    def sweep_sharded(self, mus):
+        """Multi-GPU online sweep: every rank solves + estimates its slice of ``mus`` and the ranks
+        exchange only the estimator maximum.  Returns ``(U_local, eta_local, (lo, hi), eta_max, argmax)`` with ``argmax``
+        the index into the *global* batch."""
+        from .distributed import gather_estimator_max, mu_slice, rank_and_world
+        torch = _torch()
+        mus = np.asarray(mus, dtype=np.float64)
+        rank, world = rank_and_world()
+        lo, hi = mu_slice(len(mus), rank, world)
+        theta = torch.from_numpy(self.thetas(mus[lo:hi])).cuda()
+        u, eta, info = self.sweep_device(theta)
+        self._check_info(info)
+        mx, am = self.eta_max_device(eta)
+        eta_max, argmax = gather_estimator_max(mx, am, lo)
+        return ReducedVectorArray(u, self.block_dims), eta, (lo, hi), eta_max, argmax
+
     def sweep(self, mus, decompose=False):
         """Solve and estimate a parameter batch in one call: ``(U, eta)`` or ``(U, eta, (nc, r, df), indicators)``."""
         torch = _torch()

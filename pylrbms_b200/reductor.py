@@ -27,8 +27,8 @@ from __future__ import annotations
 
 import numpy as np
 
-from . import _lib
 from ._lib import Handle, make_project_plan, make_spmm_plan
+from .distributed import exchange_regions, owner_rank, rank_and_world, region_layout
 from .kernels import project_desc, spmm_desc
 from .operators import (BlockColumnOperator, BlockEmbeddingOperator, BlockOperator, BlockProjectionOperator,
                         BlockRowOperator, Concatenation, CsrOperator, LincombOperator, VectorFunctional)
@@ -201,15 +201,7 @@ class _Planner:
     def finalize(self):
         """Allocate the output buffer, resolve tokens to offsets, create the plans."""
         torch = _torch()
-        region = [0] * self.world
-        for (r, size) in self._pending:
-            region[r] += size
-        starts = np.concatenate([[0], np.cumsum(region)]).astype(np.int64)
-        cursor = starts[:-1].copy()
-        self.offsets = np.zeros(len(self._pending), dtype=np.int64)
-        for t, (r, size) in enumerate(self._pending):
-            self.offsets[t] = cursor[r]
-            cursor[r] += size
+        self.offsets, starts = region_layout(self._pending, self.world)
         self.region_starts = starts
         self.out = torch.zeros(max(1, int(starts[-1])), dtype=torch.float64, device='cuda')
         base = self.out.data_ptr()
@@ -230,16 +222,8 @@ class _Planner:
 
     def exchange(self):
         """Multi-GPU: every rank broadcasts its contiguous result region (an all-gather of disjoint reduced blocks)."""
-        if self.world == 1:
-            return
-        import torch.distributed as dist
-        works = []
-        for r in range(self.world):
-            a, b = int(self.region_starts[r]), int(self.region_starts[r + 1])
-            if b > a:
-                works.append(dist.broadcast(self.out[a:b], src=r, async_op=True))
-        for w in works:
-            w.wait()
+        if self.world > 1:
+            exchange_regions(self.out, self.region_starts)
 
     # -- accounting for bench / roofline
     def stats(self):
@@ -406,12 +390,7 @@ class LRBMSReductor(GenericRBSystemReductor):
 
     # -- sharding of subdomains over ranks: contiguous strips
     def _shard_info(self):
-        if not self.shard:
-            return 0, 1
-        import torch.distributed as dist
-        if not (dist.is_available() and dist.is_initialized()):
-            return 0, 1
-        return dist.get_rank(), dist.get_world_size()
+        return rank_and_world() if self.shard else (0, 1)
 
     def build_plan(self):
         """Plan the whole offline projection for the current bases (no kernel runs yet)."""
@@ -420,7 +399,7 @@ class LRBMSReductor(GenericRBSystemReductor):
         subs = d.solution_space.subspaces
         S = len(subs)
         rank, world = self._shard_info()
-        owner_rank_of = (lambda owner: min(world - 1, int(owner) * world // S)) if world > 1 else None
+        owner_rank_of = (lambda owner: owner_rank(owner, S, world)) if world > 1 else None
         planner = _Planner(Handle.get(), owner_rank_of, rank, world)
         N = [len(self.bases[s.id]) for s in subs]
         V = [_ArrayRef.of(self.bases[s.id]) for s in subs]

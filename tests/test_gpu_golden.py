@@ -1,0 +1,48 @@
+"""The CUDA path against the committed golden vectors (tests/golden/*.npz, oracle outputs on seeded inputs)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, 'golden'))
+import make_golden  # noqa: E402
+
+RTOL = 1e-10
+
+
+@pytest.mark.parametrize('name', sorted(make_golden.CASES))
+def test_cuda_path_reproduces_golden(handle, name):
+    from pylrbms_b200 import LRBMSReductor, discretize
+    from pylrbms_b200.operators import LincombOperator
+    gold = np.load(os.path.join(HERE, 'golden', name + '.npz'))
+    data, bases = make_golden.build_case(name)
+    assert make_golden.input_digest(data, bases) == str(gold['input_sha256'])
+    S = data.num_subdomains
+    rd = LRBMSReductor(discretize(data)[0], bases={'domain_%d' % i: bases[i] for i in range(S)}).reduce()
+    assert list(gold['block_dims']) == rd.block_dims
+    checked = 0
+    for key in gold.files:
+        if not key.startswith('red__'):
+            continue
+        _, opname, q = key.split('__')
+        op = rd.products[opname[len('product_'):]] if opname.startswith('product_') else rd.operators[opname]
+        term = op.operators[int(q)] if isinstance(op, LincombOperator) else op
+        ref = gold[key]
+        got = term.to_dense()
+        assert got.shape == ref.shape, key
+        assert np.abs(got - ref).max() <= RTOL * max(np.abs(ref).max(), 1e-300), key
+        checked += 1
+    assert checked >= 10 * S
+    mus = gold['mus']
+    U, eta, parts, ind = rd.sweep(mus, decompose=True)
+    assert np.abs(U.data - gold['U']).max() <= 1e-9 * np.abs(gold['U']).max()
+    assert np.abs(eta - gold['eta']).max() <= RTOL * np.abs(gold['eta']).max()
+    gp = gold['parts']                                          # (n_mu, 3, S)
+    r_floor = np.abs(rd.estimator.local_eta_rf_squared * rd.estimator.r_scale()).max()
+    for kind in range(3):
+        scale = max(np.abs(gp[:, kind]).max(), r_floor if kind == 1 else 0.0)
+        assert np.abs(parts[kind].T - gp[:, kind]).max() <= RTOL * scale
+    assert np.abs(ind.T - gold['indicators']).max() <= 10 * RTOL * np.abs(gold['indicators']).max()

@@ -1,0 +1,89 @@
+"""CPU tests of the host-side logic that needs no GPU: parameter functionals, batch parsing, sharding arithmetic,
+the fixture generator's structure and bench.py's flop model."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_parameter_functionals_single_and_batched():
+    from pylrbms_b200.parameters import (ExpressionParameterFunctional, ProductParameterFunctional,
+                                         ProjectionParameterFunctional, parse_parameter, parse_parameter_batch)
+    pt = {'diffusion': (1,)}
+    one = ExpressionParameterFunctional('1.', pt)
+    dif = ExpressionParameterFunctional('diffusion', pt)
+    lt = ExpressionParameterFunctional('1.1 + sin(diffusion)', pt)         # local_thermalblock_problem.py:50-51
+    mu = parse_parameter(0.3, pt)
+    assert mu['diffusion'].shape == (1,) and one.evaluate(mu) == 1.0 and dif.evaluate(mu) == 0.3
+    assert abs(lt.evaluate(mu) - (1.1 + np.sin(0.3))) < 1e-15
+    prod = ProductParameterFunctional([dif, lt])
+    assert abs(prod.evaluate(mu) - 0.3 * (1.1 + np.sin(0.3))) < 1e-15
+    mus = np.linspace(0.1, 1.0, 11)
+    batch, n = parse_parameter_batch(mus, pt)
+    assert n == 11
+    for f in (one, dif, lt, prod):
+        vals = f.evaluate_batch(batch, n)
+        assert vals.shape == (11,)
+        assert np.allclose(vals, [f.evaluate(parse_parameter(m, pt)) for m in mus], rtol=0, atol=1e-15)
+    # list-of-dicts and dict-of-arrays forms, multi-component parameters (thermalblock_problem.py:47-50)
+    pt2 = {'diffusion': (2, 2)}
+    proj = ProjectionParameterFunctional('diffusion', (2, 2), (1, 0))
+    arr = np.arange(12.0).reshape(3, 4)
+    b2, n2 = parse_parameter_batch(arr, pt2)
+    assert n2 == 3 and np.array_equal(proj.evaluate_batch(b2, n2), arr[:, 2])
+    assert proj.evaluate(parse_parameter(arr[1], pt2)) == arr[1, 2]
+    b3, n3 = parse_parameter_batch([parse_parameter(m, pt) for m in mus], pt)
+    assert n3 == 11 and np.array_equal(b3['diffusion'][:, 0], mus)
+    with pytest.raises(ValueError):
+        parse_parameter([1.0, 2.0], pt)
+
+
+def test_sharding_arithmetic():
+    from pylrbms_b200.distributed import mu_slice, owner_rank, region_layout, subdomains_on_rank
+    for S, world in ((64, 8), (64, 3), (5, 8), (256, 4)):
+        owners = [owner_rank(s, S, world) for s in range(S)]
+        assert owners == sorted(owners) and set(owners) <= set(range(world))          # contiguous strips
+        assert sum(len(subdomains_on_rank(S, r, world)) for r in range(world)) == S
+    for n, world in ((10000, 8), (7, 3), (1000000, 8), (3, 8)):
+        cuts = [mu_slice(n, r, world) for r in range(world)]
+        assert cuts[0][0] == 0 and cuts[-1][1] == n and all(cuts[r][1] == cuts[r + 1][0] for r in range(world - 1))
+        assert max(b - a for a, b in cuts) - min(b - a for a, b in cuts) <= 1
+    pending = [(0, 4), (1, 3), (0, 2), (2, 5), (1, 1)]
+    offsets, starts = region_layout(pending, 3)
+    assert list(starts) == [0, 6, 10, 15] and list(offsets) == [0, 6, 4, 10, 9]
+
+
+def test_fixture_structure_matches_appendix_b():
+    from pylrbms_b200.swipdg_fixture import assemble_block_swipdg, make_local_bases
+    data = assemble_block_swipdg((3, 2), 4)
+    S = data.num_subdomains
+    assert S == 6 and data.Q == 2 and data.coefficients == ['1.', 'diffusion']
+    for i in range(S):
+        assert i in data.neighborhoods[i] and data.neighborhoods[i] == sorted(data.neighborhoods[i])
+        assert data.n[i] == 6 * 16
+        for q in range(2):
+            assert (i, i) in data.lhs[q]
+            for j in data.neighbors[i]:
+                C = data.lhs[q][(i, j)]
+                # coupling blocks are populated only on interface-element rows (discretize...:560-561)
+                assert 0 < np.count_nonzero(np.diff(C.indptr)) < data.n[i] / 2
+                assert abs(C - data.lhs[q][(j, i)].T).max() < 1e-14           # symmetric IPDG
+        for k in data.neighborhoods[i]:
+            assert data.oi[(k, i)].shape == (data.n[i], data.n[k])
+            assert data.fr[0][(k, i)].shape == (data.m[i], data.n[k])
+        assert data.div[i].shape == (data.n[i], data.m[i]) and data.bb[i].shape == (data.m[i], data.m[i])
+    bases = make_local_bases(data, [3, 4, 5, 6, 7, 8], seed=0)
+    for i, V in enumerate(bases):
+        G = V @ (data.energy[i] @ V.T)
+        assert np.abs(G - np.eye(V.shape[0])).max() < 1e-10
+
+
+def test_bench_flop_model_matches_survey():
+    sys.path.insert(0, ROOT)
+    import bench
+    fl = bench.survey_flops_per_mu(8, 20, 2)
+    assert fl['n_red'] == 1280 and fl['blocks'] == 288 and fl['half_bandwidth'] == 180
+    assert abs(fl['solve'] - (0.46e6 + 41.5e6 + 0.92e6)) < 0.1e6
