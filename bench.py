@@ -164,6 +164,15 @@ def cpu_online_step(rd, mus):
     return out
 
 
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core the BLAS can take."""
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=os.cpu_count() or 1)
+    except Exception:
+        pass
+
+
 def cpu_threads():
     try:
         from threadpoolctl import threadpool_info
@@ -177,6 +186,7 @@ def run_reference(a):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
+    use_all_host_threads()
     rd, t_off = cpu_reference_model(a)
     mus = make_mus(a, 0, a.cpu_sample)
     for _ in range(max(1, a.warmup) if a.warmup else 0):
@@ -407,6 +417,7 @@ def run_b200(a):
 
 
 def cpu_baseline(a):
+    use_all_host_threads()
     rd, t_off = cpu_reference_model(a)
     mus = make_mus(a, 0, a.cpu_sample)
     cpu_online_step(rd, mus[:2])
