@@ -144,10 +144,12 @@ int lrbms_symbolic_create(int32_t n_sub, const int32_t* basis_sizes, int32_t n_b
                           const int32_t* block_j, lrbms_symbolic_t* out);
 int lrbms_symbolic_destroy(lrbms_symbolic_t s);
 /* what: 0 n_red, 1 padded n, 2 tile columns, 3 L tiles, 4 A tiles, 5 update pairs, 6 factor flops per mu,
- *       7 max targets per tile column */
+ *       7 max targets per tile column, 8 shared-memory window slots (live off-diagonal L tiles, peak) */
 int lrbms_symbolic_info(lrbms_symbolic_t s, int32_t what, int64_t* out);
 /* copy out schedule arrays (for tests): which: 0 col_ptr[ntc+1], 1 row_idx[n_tiles], 2 pair_ptr[n_tiles+ntc+1],
- * 3 pair_a, 4 pair_b, 5 a_map[n_tiles]; returns number of int32 written (<= cap) or a negative status */
+ * 3 pair_a, 4 pair_b, 5 a_map[n_tiles], 6 win_slot[n_tiles], 7 late_ptr[n_tiles+ntc], 8 win_a[pairs], 9 win_b[pairs],
+ * 10 xo_ptr[ntc+1], 11 xo_idx[n_tiles+ntc], 12 cnext[n_tiles+ntc], 13 chas[ntc], 14 cord[n_tiles+ntc];
+ * returns number of int32 written (<= cap) or a negative status */
 int64_t lrbms_symbolic_get(lrbms_symbolic_t s, int32_t which, int32_t* out, int64_t cap);
 
 /* one estimator term:  out[kind][sub][mu] += coef * theta[qa](mu) * theta[qb](mu) * xl^T M xr  */
@@ -200,6 +202,11 @@ int lrbms_online_estimate(lrbms_plan_t plan, int64_t n_mu, const double* theta, 
 /* solve + estimate in one call (the unit of work of BASELINE.json's metric) */
 int lrbms_online_sweep(lrbms_plan_t plan, int64_t n_mu, const double* theta, double* u, double* eta, double* parts,
                        double* indicators, int32_t* info, void* workspace, size_t workspace_bytes, void* stream);
+/* Developer aid: with LRBMS_SOLVE_TIMING=1 in the environment at plan creation the shared-memory solve kernel records,
+ * for CTA 0, SM-clock cycles per warp and phase ([16 warps][8 phases]: 0 metadata staging, 1 diagonal tile, 2 early
+ * updates, 3 barrier, 4 triangular solve + late update, 5 barrier, 6 backward substitution, 7 store).  Copies up to n
+ * counters to out_host and returns how many were written, or a negative status. */
+int lrbms_online_debug_timing(lrbms_plan_t plan, int64_t* out_host, int32_t n);
 /* max and argmax of eta (device outputs: max_out[1], argmax_out[1]); the per-GPU leg of the estimator-max gather */
 int lrbms_eta_max(lrbms_handle_t h, int64_t n_mu, const double* eta, double* max_out, int64_t* argmax_out, void* stream);
 

@@ -21,7 +21,7 @@ EXPORTS = [
     'lrbms_spmm_plan_create', 'lrbms_project_plan_create', 'lrbms_plan_run', 'lrbms_plan_destroy', 'lrbms_plan_info',
     'lrbms_symbolic_create', 'lrbms_symbolic_destroy', 'lrbms_symbolic_info', 'lrbms_symbolic_get',
     'lrbms_online_plan_create', 'lrbms_online_workspace_bytes', 'lrbms_online_solve', 'lrbms_online_estimate',
-    'lrbms_online_sweep', 'lrbms_eta_max',
+    'lrbms_online_sweep', 'lrbms_eta_max', 'lrbms_online_debug_timing',
 ]
 
 VEC_ONE, VEC_UI, VEC_UN, VEC_UR = 0, 1, 2, 3
@@ -107,6 +107,7 @@ def load_library():
             'lrbms_online_estimate': (C.c_int, [vp, i64, vp, vp, vp, vp, vp, vp, C.c_size_t, vp]),
             'lrbms_online_sweep': (C.c_int, [vp, i64, vp, vp, vp, vp, vp, vp, vp, C.c_size_t, vp]),
             'lrbms_eta_max': (C.c_int, [vp, i64, vp, vp, vp, vp]),
+            'lrbms_online_debug_timing': (C.c_int, [vp, vp, i32]),
         }
         for name, (res, args) in protos.items():
             fn = getattr(lib, name)          # AttributeError here = header/library mismatch
@@ -255,10 +256,13 @@ class Symbolic:
     n_pairs = property(lambda self: self.info(5))
     flops = property(lambda self: self.info(6))
     max_targets = property(lambda self: self.info(7))
+    n_win_slots = property(lambda self: self.info(8))
 
     def get(self, which):
         sizes = {0: self.n_tile_cols + 1, 1: self.n_tiles, 2: self.n_tiles + self.n_tile_cols + 1, 3: self.n_pairs,
-                 4: self.n_pairs, 5: self.n_tiles}
+                 4: self.n_pairs, 5: self.n_tiles, 6: self.n_tiles, 7: self.n_tiles + self.n_tile_cols, 8: self.n_pairs,
+                 9: self.n_pairs, 10: self.n_tile_cols + 1, 11: self.n_tiles + self.n_tile_cols,
+                 12: self.n_tiles + self.n_tile_cols, 13: self.n_tile_cols, 14: self.n_tiles + self.n_tile_cols}
         out = np.zeros(sizes[which], dtype=np.int32)
         n = self.lib.lrbms_symbolic_get(self.s, which, ptr(out), out.size)
         if n != out.size:

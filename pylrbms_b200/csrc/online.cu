@@ -257,6 +257,404 @@ solve_kernel(SolveParams P, int64_t n_mu, const double* __restrict__ theta, doub
 }
 
 // ------------------------------------------------------------------------------------------------------
+//  solve_kernel_v2: the same left-looking 8x8-tile Cholesky, restructured around shared memory.
+//
+//  v1 keeps the factor of a parameter in global scratch and walks one dependent chain of L2-latency loads per tile
+//  column (ncu: tensor pipe 20 % active, 32 GB of DRAM traffic per 10 000 parameters).  v2:
+//    * one CTA of 16 warps per SM; the *live window* of L -- off-diagonal tiles (I, K) with K < J <= I, 253 tiles
+//      for the C2 band -- stays in shared memory in DMMA operand-fragment order (one conflict-free LDS.128 per lane
+//      and operand); the factor goes to global memory only once, for the backward substitution;
+//    * software pipeline over tile columns: while warp 0 factors and inverts the diagonal tile of column J-1, all
+//      other warps already accumulate the "early" updates of column J (source columns <= J-2); the "late" update
+//      with column J-1 (one pair per target) follows the triangular solve of column J-1;
+//    * targets of a column are handed out dynamically (longest first) through a shared-memory counter;
+//    * the backward substitution streams the factor back with a 4-stage cp.async ring.
+// ------------------------------------------------------------------------------------------------------
+constexpr int kV2Threads = 512;
+constexpr int kV2Warps = kV2Threads / 32;
+constexpr int kBackStages = 6;     // backward-substitution ring; columns are prefetched kBackStages - 2 ahead
+constexpr int kMetaBufs = 4;     // column metadata is staged two columns ahead (cp.async), four buffers in flight
+constexpr int kABufs = 3;        // staged operator tiles: only needed while a column's early updates run
+
+struct SolveParamsV2 {
+  SolveParams base;
+  const int4* ccol;         // [ntc + 1] {first tile, tiles, first item, tile (J+1, J) exists}
+  const int4* ccol2;        // [ntc] {first tile pair, tile pairs, first rhs pair, rhs pairs}
+  const int4* ccol3;        // [ntc] {first staged operator tile, staged operator tiles, 0, 0}
+  const int32_t* ca_tile;   // operator tile index (into a_tiles) per staged tile
+  int32_t n_ca;             // length of ca_tile
+  const int4* cdesc;        // per item: {pair begin, late begin, pair end (staged offsets), staged operator tile or -1}
+  const int32_t* cslot;     // per item: window slot (-1: diagonal tile / rhs row)
+  const int32_t* cord;      // per item position: li in hand-out order (longest early update first)
+  const int32_t* cnext;     // per item: li of the target in the next column its tile feeds (-1: none)
+  const int2* win_ab;       // per pair: window slots of the two operands (a < 0: forward-solve row y_{-a-1})
+  int32_t region_doubles;   // shared-memory window region (also the backward-substitution ring)
+  int32_t max_targets;      // per column, incl. the diagonal tile and the rhs row
+  int32_t max_col_pairs;
+  int32_t max_a_col;
+  int32_t back_stage_doubles;
+  long long* timing;        // optional (LRBMS_SOLVE_TIMING=1): [16 warps][8 phases] SM cycles of CTA 0, else NULL
+};
+
+// acc -= sum_p A_p * B_p^T over staged pairs [p0, p1).  Eight accumulator registers = four independent DMMA chains
+// (two pairs in flight x two k halves): the dependent-issue latency of DMMA, not its throughput, is what a single
+// warp runs into.  RHS = true: the A operand is the forward-solve row y_K (row 0 of a virtual tile).
+template <bool RHS>
+__device__ __forceinline__ void apply_pairs(const int2* __restrict__ pairs, const double* __restrict__ win,
+                                            const double* __restrict__ sx, int p0, int p1, int lane, double (&acc)[8]) {
+  const int g = lane >> 2, t = lane & 3;
+  auto load_a = [&](int a) -> double2 {
+    if (!RHS) return *reinterpret_cast<const double2*>(win + a * 64 + lane * 2);
+    const int K = -a - 1;
+    return make_double2((g == 0) ? sx[8 * K + t] : 0.0, (g == 0) ? sx[8 * K + 4 + t] : 0.0);
+  };
+  int p = p0;
+#pragma unroll 2
+  for (; p + 1 < p1; p += 2) {
+    const int2 ab0 = pairs[p], ab1 = pairs[p + 1];
+    const double2 fa = load_a(ab0.x), ga = load_a(ab1.x);
+    const double2 fb = *reinterpret_cast<const double2*>(win + ab0.y * 64 + lane * 2);
+    const double2 gb = *reinterpret_cast<const double2*>(win + ab1.y * 64 + lane * 2);
+    dmma884(acc[0], acc[1], -fa.x, fb.x);
+    dmma884(acc[4], acc[5], -ga.x, gb.x);
+    dmma884(acc[2], acc[3], -fa.y, fb.y);
+    dmma884(acc[6], acc[7], -ga.y, gb.y);
+  }
+  if (p < p1) {
+    const int2 ab0 = pairs[p];
+    const double2 fa = load_a(ab0.x);
+    const double2 fb = *reinterpret_cast<const double2*>(win + ab0.y * 64 + lane * 2);
+    dmma884(acc[0], acc[1], -fa.x, fb.x);
+    dmma884(acc[2], acc[3], -fa.y, fb.y);
+  }
+}
+
+// accumulator layout (T[g][2t], T[g][2t+1]) -> operand-fragment layout (T[g][t], T[g][t+4])
+__device__ __forceinline__ double2 acc_to_frag(int lane, double x0, double x1) {
+  const int t = lane & 3;
+  const int s1 = (lane & ~3) | (t >> 1), s2 = s1 | 2;
+  const double e0 = __shfl_sync(0xffffffffu, x0, s1), e1 = __shfl_sync(0xffffffffu, x1, s1);
+  const double f0 = __shfl_sync(0xffffffffu, x0, s2), f1 = __shfl_sync(0xffffffffu, x1, s2);
+  return make_double2((t & 1) ? e1 : e0, (t & 1) ? f1 : f0);
+}
+
+__global__ void __launch_bounds__(kV2Threads, 1)
+solve_kernel_v2(SolveParamsV2 P2, int64_t n_mu, const double* __restrict__ theta, double* __restrict__ u,
+                int32_t* __restrict__ info, double* __restrict__ work) {
+  const SolveParams& P = P2.base;
+  extern __shared__ __align__(16) double smem[];
+  const int MT = P2.max_targets;
+  double* win = smem;                                         // region_doubles
+  double* acc0 = win + P2.region_doubles;                     // MT * 64
+  double* acc1 = acc0 + MT * 64;
+  double* sx = acc1 + MT * 64;                                // n_pad
+  double* sW = sx + P.n_pad;                                  // 64
+  double* sred = sW + 64;                                     // 2 * kV2Warps * 8
+  double* sth = sred + 2 * kV2Warps * 8;                      // n_theta (<= 32)
+  double* sA = sth + 32;                                      // kABufs * max_a_col * Q * 64
+  const int a_buf_doubles = P2.max_a_col * P.Q * 64;
+  int4* sDesc = reinterpret_cast<int4*>(sA + kABufs * a_buf_doubles);             // kMetaBufs * MT
+  int4* sCol = sDesc + kMetaBufs * MT;                                            // ntc + 1
+  int4* sCol2 = sCol + (P.ntc + 1);                                               // ntc
+  int4* sCol3 = sCol2 + P.ntc;                                                    // ntc
+  int2* sPair = reinterpret_cast<int2*>(sCol3 + P.ntc);                           // kMetaBufs * max_col_pairs
+  int* sSlot = reinterpret_cast<int*>(sPair + kMetaBufs * P2.max_col_pairs);      // kMetaBufs * MT
+  int* sOrd = sSlot + kMetaBufs * MT;                                             // kMetaBufs * MT
+  int* sNext = sOrd + kMetaBufs * MT;                                             // kMetaBufs * MT
+  int* sCaTile = sNext + kMetaBufs * MT;                                          // n_ca
+  __shared__ int s_info;
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  double* L = work + (int64_t)blockIdx.x * P.work_stride;
+  const bool timing = P2.timing != nullptr && blockIdx.x == 0;
+  long long tph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tlast = 0;
+#define LRBMS_TICK(k) do { if (timing) { const long long now_ = clock64(); tph[k] += now_ - tlast; tlast = now_; } } while (0)
+
+  // ---- per-column tables: loaded once per CTA, no global-memory latency inside the column loop afterwards
+  for (int i = threadIdx.x; i <= P.ntc; i += kV2Threads) sCol[i] = P2.ccol[i];
+  for (int i = threadIdx.x; i < P.ntc; i += kV2Threads) { sCol2[i] = P2.ccol2[i]; sCol3[i] = P2.ccol3[i]; }
+  for (int i = threadIdx.x; i < P2.n_ca; i += kV2Threads) sCaTile[i] = P2.ca_tile[i];
+  __syncthreads();
+
+  // stage everything column Jn needs into buffer Jn % kMetaBufs / Jn % kABufs.  Called by ONE producer warp (the
+  // address arithmetic is a long dependent chain; keeping it off the other 15 warps takes it off the critical path);
+  // asynchronous copies, one commit group per call
+  auto stage_meta = [&](int Jn) {
+    if (Jn < P.ntc) {
+      const int b = Jn % kMetaBufs;
+      const int4 col = sCol[Jn];
+      const int4 ci = sCol2[Jn];
+      const int4 c3 = sCol3[Jn];
+      for (int i = lane; i <= col.y; i += 32) {
+        cp_async16(sDesc + b * MT + i, P2.cdesc + col.z + i);
+        cp_async4(sSlot + b * MT + i, P2.cslot + col.z + i);
+        cp_async4(sOrd + b * MT + i, P2.cord + col.z + i);
+        cp_async4(sNext + b * MT + i, P2.cnext + col.z + i);
+      }
+      int2* dst = sPair + b * P2.max_col_pairs;
+      for (int i = lane; i < ci.y; i += 32) cp_async8(dst + i, P2.win_ab + ci.x + i);
+      for (int i = lane; i < ci.w; i += 32) cp_async8(dst + ci.y + i, P2.win_ab + ci.z + i);
+      // raw operator tiles A_q of the column's targets (the theta-weighted sum is formed when they are consumed):
+      // one 16-byte chunk per lane, 32 lanes = one tile per step
+      double* adst = sA + (Jn % kABufs) * a_buf_doubles;
+      for (int k = 0; k < c3.y; ++k) {
+        const int64_t src_tile = sCaTile[c3.x + k];
+        for (int q = 0; q < P.Q; ++q)
+          cp_async16(adst + (k * P.Q + q) * 64 + lane * 2, P.a_tiles + ((int64_t)q * P.n_a_tiles + src_tile) * 64 + lane * 2);
+      }
+    }
+    cp_async_commit();
+  };
+  constexpr int kProducer = kV2Warps - 1;
+
+  for (int64_t mu = blockIdx.x; mu < n_mu; mu += gridDim.x) {
+    __syncthreads();
+    for (int q = threadIdx.x; q < P.n_theta; q += kV2Threads) sth[q] = theta[mu * P.n_theta + q];
+    if (threadIdx.x == 0) s_info = 0;
+    if (warp == kProducer) { stage_meta(0); stage_meta(1); }
+    cp_async_wait<0>();
+    __syncthreads();
+    double* accC = acc0;
+    double* accP = acc1;
+    if (timing) tlast = clock64();
+
+    for (int J = 0; J <= P.ntc; ++J) {
+      if (warp == kProducer) stage_meta(J + 2);
+      LRBMS_TICK(0);
+      const int mb = J % kMetaBufs, mbp = (J + kMetaBufs - 1) % kMetaBufs;
+      const int4* descC = sDesc + mb * MT;
+      const int2* pairC = sPair + mb * P2.max_col_pairs;
+      const int4 colC = sCol[J];                                   // (J == ntc: empty column)
+      const int4 colP = sCol[J > 0 ? J - 1 : 0];
+      const int has_next = (J >= 1 && J < P.ntc) ? colP.w : 0;
+      double2 fbn_keep = make_double2(0.0, 0.0);
+      // ---------------- diagonal tile of column J-1 (warp 0): Cholesky by row operations on [A | I] held one row per
+      //                  lane, so L^{-1} (what the triangular solves multiply with) falls out of the same eight steps
+      if (warp == 0 && J >= 1) {
+        const int Jp = J - 1;
+        const int i = lane & 7;
+        double a[8], w[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { a[j] = accP[i * 8 + j]; w[j] = (j == i) ? 1.0 : 0.0; }
+        int bad = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          double akk = __shfl_sync(0xffffffffu, a[k], k);
+          if (8 * Jp + k >= P.n_red) akk = 1.0;                  // padding rows: identity
+          if (!(akk > 0.0)) { if (!bad) bad = 8 * Jp + k + 1; akk = 1.0; }
+          const double r = rsqrt(akk);
+          const double lik = ((i == k) ? akk : a[k]) * r;        // L[i][k] for i >= k
+          a[k] = lik;
+          double pj[8], wj[8];
+#pragma unroll
+          for (int j = k + 1; j < 8; ++j) pj[j] = __shfl_sync(0xffffffffu, lik, j);      // L[j][k]
+#pragma unroll
+          for (int j = 0; j <= k; ++j) wj[j] = __shfl_sync(0xffffffffu, w[j], k) * r;    // scaled pivot row of W
+          if (i > k) {
+#pragma unroll
+            for (int j = k + 1; j < 8; ++j) a[j] -= lik * pj[j];
+#pragma unroll
+            for (int j = 0; j <= k; ++j) w[j] -= lik * wj[j];
+          } else if (i == k) {
+#pragma unroll
+            for (int j = 0; j <= k; ++j) w[j] = wj[j];
+          }
+        }
+        if (bad && lane == 0 && s_info == 0) s_info = bad;
+        if (lane < 8) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const double v = (j <= i) ? w[j] : 0.0;
+            sW[i * 8 + j] = v;
+            L[(int64_t)colP.x * 64 + i * 8 + j] = v;           // the diagonal slot of the stored factor holds L_JJ^{-1}
+          }
+        }
+      }
+      LRBMS_TICK(1);
+      // ---------------- early updates of column J (source columns <= J-2), dealt to the 15 update warps
+      if (J < P.ntc && warp > 0) {
+        const int ncol = colC.y;
+        const int* ordC = sOrd + mb * MT;
+        const double* aC = sA + (J % kABufs) * a_buf_doubles;
+        // snake deal (warp 0 is busy with the diagonal tile): round r hands items 15 r .. 15 r + 14 to warps 1..15
+        // (r even) or 15..1 (r odd), longest items first
+        for (int r = 0; 15 * r <= ncol; ++r) {
+          const int item = 15 * r + ((r & 1) ? (15 - warp) : (warp - 1));
+          if (item > ncol) break;
+          const int li = ordC[item];
+          const int4 d = descC[li];
+          double2 v0 = make_double2(0.0, 0.0), v1 = v0;           // rhs row: loads issued first, consumed last
+          if (li == ncol && g == 0) {
+            v0 = __ldg(reinterpret_cast<const double2*>(P.rhs + 8 * J + 2 * t));
+            if (P.Qf > 1) v1 = __ldg(reinterpret_cast<const double2*>(P.rhs + P.n_pad + 8 * J + 2 * t));
+          }
+          double acc[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) acc[k] = 0.0;
+          if (li < ncol) apply_pairs<false>(pairC, win, sx, d.x, d.y, lane, acc);
+          else apply_pairs<true>(pairC, win, sx, d.x, d.y, lane, acc);
+          double a0 = 0.0, a1 = 0.0;
+          if (li < ncol) {
+            if (d.w >= 0) {                                        // A(mu) tile = sum_q theta_q A_q, left to right
+              const double* at = aC + d.w * P.Q * 64 + g * 8 + 2 * t;
+              for (int q = 0; q < P.Q; ++q) {
+                const double2 v = *reinterpret_cast<const double2*>(at + q * 64);
+                if (q == 0) { a0 = sth[0] * v.x; a1 = sth[0] * v.y; }
+                else { a0 += sth[q] * v.x; a1 += sth[q] * v.y; }
+              }
+            }
+          } else {
+            a0 = sth[P.Q] * v0.x; a1 = sth[P.Q] * v0.y;
+            if (P.Qf > 1) { a0 += sth[P.Q + 1] * v1.x; a1 += sth[P.Q + 1] * v1.y; }
+            for (int q = 2; q < P.Qf && g == 0; ++q) {
+              const double2 v = __ldg(reinterpret_cast<const double2*>(P.rhs + (int64_t)q * P.n_pad + 8 * J + 2 * t));
+              a0 += sth[P.Q + q] * v.x; a1 += sth[P.Q + q] * v.y;
+            }
+          }
+          *reinterpret_cast<double2*>(accC + li * 64 + lane * 2) =
+              make_double2(a0 + ((acc[0] + acc[4]) + (acc[2] + acc[6])), a1 + ((acc[1] + acc[5]) + (acc[3] + acc[7])));
+        }
+      }
+      LRBMS_TICK(2);
+      __syncthreads();   // B1: W_{J-1} ready, early sums of column J stored
+      LRBMS_TICK(3);
+      // ---------------- column J-1: triangular solve L_IJ = C_IJ L_JJ^{-T} (rhs row likewise), fused with the "late"
+      //                  update of column J: target (I, J) -= L_{I,J-1} L_{J,J-1}^T, done by the warp that just formed L_{I,J-1}
+      if (J >= 1) {
+        const int Jp = J - 1;
+        const int cp0 = colP.x, ncol = colP.y;
+        const int* slotP = sSlot + mbp * MT;
+        const int* nextP = sNext + mbp * MT;
+        // Slot 0: L_{J,J-1} (every warp forms it itself instead of waiting for another warp); slots 1, 2: two of this
+        // warp's own items.  The three solves are independent, written side by side so their latencies overlap.
+        for (int base = 1 + warp; base <= ncol || base == 1 + warp; base += 2 * kV2Warps) {
+          int li[3] = {1, base, base + kV2Warps};
+          bool on[3] = {has_next != 0 && base == 1 + warp && base <= ncol, base <= ncol, base + kV2Warps <= ncol};
+          if (!on[0] && !on[1]) break;
+          double2 c[3], cc[3];
+          int nl[3];
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            c[k] = on[k] ? *reinterpret_cast<const double2*>(accP + li[k] * 64 + lane * 2) : make_double2(0.0, 0.0);
+            nl[k] = (k > 0 && on[k] && has_next) ? nextP[li[k]] : -1;
+            cc[k] = (nl[k] >= 0) ? *reinterpret_cast<const double2*>(accC + nl[k] * 64 + lane * 2) : make_double2(0.0, 0.0);
+          }
+          double x0[3] = {0.0, 0.0, 0.0}, x1[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+          for (int kk = 0; kk < 2; ++kk) {
+            const int src = (lane & ~3) | (2 * kk + (t >> 1));
+            const double b = sW[g * 8 + 4 * kk + t];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+              const double v0 = __shfl_sync(0xffffffffu, c[k].x, src);
+              const double v1 = __shfl_sync(0xffffffffu, c[k].y, src);
+              dmma884(x0[k], x1[k], (t & 1) ? v1 : v0, b);
+            }
+          }
+          double2 frag[3];
+#pragma unroll
+          for (int k = 0; k < 3; ++k) frag[k] = acc_to_frag(lane, x0[k], x1[k]);
+          if (base == 1 + warp) fbn_keep = frag[0];
+#pragma unroll
+          for (int k = 1; k < 3; ++k) {
+            if (!on[k]) continue;
+            if (li[k] < ncol) {
+              *reinterpret_cast<double2*>(win + slotP[li[k]] * 64 + lane * 2) = frag[k];
+              *reinterpret_cast<double2*>(L + (int64_t)(cp0 + li[k]) * 64 + lane * 2) = frag[k];
+            } else if (g == 0) {
+              sx[8 * Jp + 2 * t] = x0[k];
+              sx[8 * Jp + 2 * t + 1] = x1[k];
+            }
+            if (nl[k] >= 0) {
+              double n0 = 0.0, n1 = 0.0;
+              dmma884(cc[k].x, cc[k].y, -frag[k].x, fbn_keep.x);
+              dmma884(n0, n1, -frag[k].y, fbn_keep.y);
+              *reinterpret_cast<double2*>(accC + nl[k] * 64 + lane * 2) = make_double2(cc[k].x + n0, cc[k].y + n1);
+            }
+          }
+        }
+      }
+      LRBMS_TICK(4);
+      cp_async_wait<1>();   // everything staged for column J+1 has landed (column J+2 may still be in flight)
+      __syncthreads();      // B2: column J-1 of L, y_{J-1} and the completed targets of column J visible
+      LRBMS_TICK(5);
+      double* tmp = accC; accC = accP; accP = tmp;
+    }
+    cp_async_wait<0>();
+
+    // ---------------- backward substitution  L^T u = y: the factor streams back through a cp.async ring; one
+    //                  barrier per tile column, every warp finishes u_J redundantly from the partial sums
+    {
+      const int stage = P2.back_stage_doubles;
+      auto issue = [&](int Jc) {
+        if (Jc >= 0) {
+          const int4 col = sCol[Jc];
+          double* dst = win + ((P.ntc - 1 - Jc) % kBackStages) * stage;
+          const double* src = L + (int64_t)col.x * 64;
+          for (int c = threadIdx.x; c < col.y * 32; c += kV2Threads) cp_async16(dst + 2 * c, src + 2 * c);
+          int* rdst = sSlot + ((P.ntc - 1 - Jc) % kBackStages) * MT;   // sSlot/sOrd/sNext are free now: 12 MT ints
+          if (threadIdx.x < col.y) cp_async4(rdst + threadIdx.x, P.row_idx + col.x + threadIdx.x);
+        }
+        cp_async_commit();
+      };
+      // A ring slot is refilled only two barriers after its last reader: prefetch distance kBackStages - 2
+      for (int s = 0; s < kBackStages - 2; ++s) issue(P.ntc - 1 - s);
+      cp_async_wait<kBackStages - 3>();       // column ntc-1 has landed
+      __syncthreads();
+      for (int J = P.ntc - 1; J >= 0; --J) {
+        issue(J - (kBackStages - 2));
+        const int bsel = (P.ntc - 1 - J) % kBackStages;
+        const double* buf = win + bsel * stage;
+        const int* rows = sSlot + bsel * MT;
+        const int ncol = sCol[J].y;
+        double s0 = 0.0, s1 = 0.0;       // partial sums for solution components t and t + 4
+        for (int li = 1 + warp; li < ncol; li += kV2Warps) {
+          const double2 f = *reinterpret_cast<const double2*>(buf + li * 64 + lane * 2);
+          const double xv = sx[8 * rows[li] + g];
+          s0 += f.x * xv;
+          s1 += f.y * xv;
+        }
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) {
+          s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+          s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        }
+        double* red = sred + (J & 1) * kV2Warps * 8;
+        if (g == 0) { red[warp * 8 + t] = s0; red[warp * 8 + 4 + t] = s1; }
+        cp_async_wait<kBackStages - 3>();     // column J-1 has landed (needed right after the barrier)
+        __syncthreads();
+        {
+          // lane (q, c), q = lane >> 3: sums four of the sixteen partials of component c, then a two-step butterfly
+          const int cidx = lane & 7, q4 = lane >> 3;
+          const double* rq = red + (q4 * 4) * 8 + cidx;
+          double part = (rq[0] + rq[8]) + (rq[16] + rq[24]);
+          part += __shfl_xor_sync(0xffffffffu, part, 8);
+          part += __shfl_xor_sync(0xffffffffu, part, 16);
+          const double v = sx[8 * J + cidx] - part;            // lanes c, c + 8, c + 16, c + 24 all hold v_c
+          // u_c = sum_k W[k][c] v_k: lane (q, c) takes k = 2q, 2q + 1
+          double accv = buf[(2 * q4) * 8 + cidx] * __shfl_sync(0xffffffffu, v, 2 * q4) +
+                        buf[(2 * q4 + 1) * 8 + cidx] * __shfl_sync(0xffffffffu, v, 2 * q4 + 1);
+          accv += __shfl_xor_sync(0xffffffffu, accv, 8);
+          accv += __shfl_xor_sync(0xffffffffu, accv, 16);
+          if (lane < 8) sx[8 * J + cidx] = accv;     // every warp writes the same values: no second barrier needed
+          __syncwarp();
+        }
+      }
+      cp_async_wait<0>();
+      __syncthreads();
+    }
+    LRBMS_TICK(6);
+    for (int i = threadIdx.x; i < P.n_red; i += kV2Threads) u[mu * P.n_red + i] = sx[i];
+    if (threadIdx.x == 0 && info) info[mu] = s_info;
+    LRBMS_TICK(7);
+  }
+  if (timing && lane == 0)
+    for (int k = 0; k < 8; ++k) P2.timing[warp * 8 + k] = tph[k];
+#undef LRBMS_TICK
+}
+
+// ------------------------------------------------------------------------------------------------------
 //  estimator
 // ------------------------------------------------------------------------------------------------------
 constexpr int kEstThreads = 256;
@@ -461,6 +859,10 @@ __global__ void eta_max_kernel(int64_t n, const double* __restrict__ eta, double
 struct OnlinePlan : lrbms_plan {
   lrbms_symbolic sym;
   SolveParams sp;
+  SolveParamsV2 sp2;
+  bool use_v2 = false;
+  size_t solve2_smem = 0;
+  int64_t solve_stride = 0;     // doubles of factor scratch per resident CTA of the selected solve kernel
   EstParams ep;
   CombineParams cp;
   int solve_grid = 0;
@@ -561,6 +963,54 @@ int lrbms_online_plan_create(lrbms_handle_t h, const lrbms_reduced_system_t* sys
     P->solve_grid = per_sm * h->sm_count;
   }
 
+  P->solve_stride = sp.work_stride;
+  // ---- shared-memory-window kernel (v2): used whenever the live window of L fits into shared memory
+  {
+    const int maxcol = std::max(1, S.max_targets - 1);
+    const int MT = S.max_targets;
+    const int64_t region = std::max<int64_t>((int64_t)S.n_win_slots * 64, (int64_t)kBackStages * maxcol * 64);
+    const int mcp = std::max(1, S.max_col_pairs), mac = std::max(1, S.max_a_col);
+    const size_t bytes = sizeof(double) * ((size_t)region + 2 * (size_t)MT * 64 + S.n_pad + 64 + 2 * kV2Warps * 8 + 32 +
+                                           (size_t)kABufs * mac * Q * 64) +
+                         16 * ((size_t)kMetaBufs * MT + (size_t)(S.ntc + 1) + 2 * (size_t)S.ntc) + 8 * (size_t)kMetaBufs * mcp +
+                         4 * (3 * (size_t)kMetaBufs * MT + S.ca_tile.size()) + 64;
+    const char* force_v1 = getenv("LRBMS_SOLVE_V1");
+    if (bytes <= (size_t)h->max_smem_optin && !(force_v1 && atoi(force_v1) > 0)) {
+      SolveParamsV2& s2 = P->sp2;
+      s2.base = sp;
+      s2.base.work_stride = (int64_t)S.n_tiles() * 64;
+      s2.region_doubles = (int32_t)region;
+      s2.max_targets = MT;
+      s2.max_col_pairs = mcp;
+      s2.max_a_col = mac;
+      s2.back_stage_doubles = maxcol * 64;
+      s2.n_ca = (int32_t)S.ca_tile.size();
+      UP_I32(s2.cslot, S.cslot);
+      UP_I32(s2.cord, S.cord);
+      UP_I32(s2.cnext, S.cnext);
+      UP_I32(s2.ca_tile, S.ca_tile);
+      const int32_t* tmp = nullptr;
+      UP_I32(tmp, S.ccol);   s2.ccol = reinterpret_cast<const int4*>(tmp);
+      UP_I32(tmp, S.cinfo);  s2.ccol2 = reinterpret_cast<const int4*>(tmp);
+      UP_I32(tmp, S.ccol3);  s2.ccol3 = reinterpret_cast<const int4*>(tmp);
+      UP_I32(tmp, S.cdesc);  s2.cdesc = reinterpret_cast<const int4*>(tmp);
+      UP_I32(tmp, S.win_ab); s2.win_ab = reinterpret_cast<const int2*>(tmp);
+      s2.timing = nullptr;
+      if (const char* tenv = getenv("LRBMS_SOLVE_TIMING")) {
+        if (atoi(tenv) > 0) {
+          rc = plan_alloc(P, &s2.timing, (size_t)kV2Warps * 8);
+          if (rc) { lrbms_plan_destroy(P); return rc; }
+          cudaMemset(s2.timing, 0, sizeof(long long) * kV2Warps * 8);
+        }
+      }
+      P->solve2_smem = bytes;
+      LRBMS_CUDA_CHECK(h, cudaFuncSetAttribute(solve_kernel_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+      P->use_v2 = true;
+      P->solve_grid = h->sm_count;
+      P->solve_stride = s2.base.work_stride;
+    }
+  }
+
   // ---- estimator tables
   P->has_estimator = sys->n_terms > 0;
   if (P->has_estimator) {
@@ -640,7 +1090,7 @@ int lrbms_online_plan_create(lrbms_handle_t h, const lrbms_reduced_system_t* sys
 
 static size_t solve_ws_bytes(const OnlinePlan* P, int64_t n_mu) {
   const int64_t ctas = std::min<int64_t>(P->solve_grid, std::max<int64_t>(1, n_mu));
-  return (size_t)ctas * P->sp.work_stride * sizeof(double);
+  return (size_t)ctas * P->solve_stride * sizeof(double);
 }
 static size_t parts_ws_bytes(const OnlinePlan* P, int64_t n_mu) {
   return (size_t)3 * P->sym.n_sub * std::max<int64_t>(1, n_mu) * sizeof(double);
@@ -661,7 +1111,10 @@ int lrbms_online_solve(lrbms_plan_t plan, int64_t n_mu, const double* theta, dou
   if (n_mu <= 0) return LRBMS_OK;
   LRBMS_REQUIRE(P->ctx, workspace_bytes >= solve_ws_bytes(P, n_mu), "online_solve: workspace too small (see lrbms_online_workspace_bytes)");
   const int grid = (int)std::min<int64_t>(P->solve_grid, n_mu);
-  solve_kernel<<<grid, kSolveThreads, P->solve_smem, (cudaStream_t)stream>>>(P->sp, n_mu, theta, u, info, (double*)workspace);
+  if (P->use_v2)
+    solve_kernel_v2<<<grid, kV2Threads, P->solve2_smem, (cudaStream_t)stream>>>(P->sp2, n_mu, theta, u, info, (double*)workspace);
+  else
+    solve_kernel<<<grid, kSolveThreads, P->solve_smem, (cudaStream_t)stream>>>(P->sp, n_mu, theta, u, info, (double*)workspace);
   LRBMS_CUDA_CHECK(P->ctx, cudaGetLastError());
   return LRBMS_OK;
 }
@@ -691,6 +1144,15 @@ int lrbms_online_sweep(lrbms_plan_t plan, int64_t n_mu, const double* theta, dou
   int rc = lrbms_online_solve(plan, n_mu, theta, u, info, workspace, workspace_bytes, stream);
   if (rc) return rc;
   return lrbms_online_estimate(plan, n_mu, theta, u, eta, parts, indicators, workspace, workspace_bytes, stream);
+}
+
+int lrbms_online_debug_timing(lrbms_plan_t plan, int64_t* out_host, int32_t n) {
+  if (!plan || plan->kind != PLAN_ONLINE || !out_host) return LRBMS_ERR_INVALID;
+  OnlinePlan* P = static_cast<OnlinePlan*>(plan);
+  if (!P->use_v2 || !P->sp2.timing) return lrbms_fail(P->ctx, LRBMS_ERR_INVALID, "debug timing is off (set LRBMS_SOLVE_TIMING=1 before creating the plan)");
+  const int cnt = std::min<int>(n, kV2Warps * 8);
+  LRBMS_CUDA_CHECK(P->ctx, cudaMemcpy(out_host, P->sp2.timing, sizeof(long long) * cnt, cudaMemcpyDeviceToHost));
+  return cnt;
 }
 
 int lrbms_eta_max(lrbms_handle_t h, int64_t n_mu, const double* eta, double* max_out, int64_t* argmax_out, void* stream) {

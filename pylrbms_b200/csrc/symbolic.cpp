@@ -135,6 +135,125 @@ int lrbms_symbolic_build(lrbms_symbolic& S, int32_t n_sub, const int32_t* sizes,
       ++fill[tgt];
     }
   }
+  // ---- shared-memory window schedule (solve_kernel_v2)
+  {
+    S.win_slot.assign(n_tiles, -1);
+    std::vector<std::vector<int32_t>> by_row(S.ntc);
+    for (int J = 0; J < S.ntc; ++J)
+      for (int32_t p = S.col_ptr[J] + 1; p < S.col_ptr[J + 1]; ++p) by_row[S.row_idx[p]].push_back(p);
+    std::vector<int32_t> free_slots;
+    S.n_win_slots = 0;
+    for (int J = 0; J < S.ntc; ++J) {
+      // tiles (J, K) were last read while column J was formed; column J's own tiles are written after that
+      for (int32_t p : by_row[J]) free_slots.push_back(S.win_slot[p]);
+      for (int32_t p = S.col_ptr[J] + 1; p < S.col_ptr[J + 1]; ++p) {
+        if (!free_slots.empty()) { S.win_slot[p] = free_slots.back(); free_slots.pop_back(); }
+        else S.win_slot[p] = S.n_win_slots++;
+      }
+    }
+    S.late_ptr.assign(n_targets, 0);
+    auto set_late = [&](int64_t tgt, int J) {
+      int32_t lp = S.pair_ptr[tgt + 1];
+      if (J >= 1) {
+        const int32_t lim = S.col_ptr[J - 1];
+        lp = S.pair_ptr[tgt];
+        while (lp < S.pair_ptr[tgt + 1] && S.pair_b[lp] < lim) ++lp;
+      }
+      S.late_ptr[tgt] = lp;
+    };
+    S.xo_ptr.assign(S.ntc + 1, 0);
+    S.xo_idx.clear();
+    for (int J = 0; J < S.ntc; ++J) {
+      std::vector<int32_t> items;
+      for (int32_t p = S.col_ptr[J]; p < S.col_ptr[J + 1]; ++p) { set_late(p, J); items.push_back(p); }
+      set_late(n_tiles + J, J);
+      items.push_back((int32_t)(n_tiles + J));
+      std::stable_sort(items.begin(), items.end(), [&](int32_t a, int32_t b) {
+        return (S.late_ptr[a] - S.pair_ptr[a]) > (S.late_ptr[b] - S.pair_ptr[b]);
+      });
+      S.xo_idx.insert(S.xo_idx.end(), items.begin(), items.end());
+      S.xo_ptr[J + 1] = (int32_t)S.xo_idx.size();
+    }
+    S.win_a.assign(total, 0);
+    S.win_b.assign(total, 0);
+    S.win_ab.assign(2 * total, 0);
+    for (int64_t p = 0; p < total; ++p) {
+      const int32_t a = S.pair_a[p];
+      S.win_a[p] = (a < n_tiles) ? S.win_slot[a] : -(int32_t)(a - n_tiles + 1);
+      S.win_b[p] = S.win_slot[S.pair_b[p]];
+      S.win_ab[2 * p] = S.win_a[p];
+      S.win_ab[2 * p + 1] = S.win_b[p];
+    }
+    const int64_t n_items_total = S.xo_ptr[S.ntc];
+    S.cdesc.assign(4 * n_items_total, 0);
+    S.cslot.assign(n_items_total, -1);
+    S.cord.assign(n_items_total, 0);
+    S.cinfo.assign(4 * (int64_t)S.ntc, 0);
+    S.max_col_pairs = 0;
+    for (int J = 0; J < S.ntc; ++J) {
+      const int32_t cp0 = S.col_ptr[J], ncol = S.col_ptr[J + 1] - cp0, xo0 = S.xo_ptr[J];
+      const int32_t tp0 = S.pair_ptr[cp0], tpn = S.pair_ptr[cp0 + ncol] - tp0;
+      const int64_t rt = n_tiles + J;
+      const int32_t rp0 = S.pair_ptr[rt], rpn = S.pair_ptr[rt + 1] - rp0;
+      S.cinfo[4 * J] = tp0; S.cinfo[4 * J + 1] = tpn; S.cinfo[4 * J + 2] = rp0; S.cinfo[4 * J + 3] = rpn;
+      S.max_col_pairs = std::max(S.max_col_pairs, tpn + rpn);
+      for (int li = 0; li <= ncol; ++li) {
+        const int64_t tgt = (li < ncol) ? (cp0 + li) : rt;
+        const int32_t shift = (li < ncol) ? tp0 : (rp0 - tpn);
+        int32_t* d = &S.cdesc[4 * (int64_t)(xo0 + li)];
+        d[0] = S.pair_ptr[tgt] - shift;
+        d[1] = S.late_ptr[tgt] - shift;
+        d[2] = S.pair_ptr[tgt + 1] - shift;
+        d[3] = (li < ncol) ? S.a_map[tgt] : -1;
+        S.cslot[xo0 + li] = (li < ncol) ? S.win_slot[tgt] : -1;
+      }
+      // hand-out order of the early updates: longest item first (the kernel deals them to its 15 update warps in
+      // snake order: 1..15, 15..1, ...)
+      for (int it = 0; it <= ncol; ++it) {
+        const int32_t tgt = S.xo_idx[xo0 + it];
+        S.cord[xo0 + it] = (tgt < n_tiles) ? (tgt - cp0) : ncol;
+      }
+    }
+    // operator tiles staged per column (only the items that carry one)
+    S.ccol3.assign(4 * (int64_t)S.ntc, 0);
+    S.ca_tile.clear();
+    S.max_a_col = 0;
+    for (int J = 0; J < S.ntc; ++J) {
+      const int32_t cp0 = S.col_ptr[J], ncol = S.col_ptr[J + 1] - cp0, xo0 = S.xo_ptr[J];
+      S.ccol3[4 * J] = (int32_t)S.ca_tile.size();
+      int32_t na = 0;
+      for (int li = 0; li < ncol; ++li) {
+        int32_t& w = S.cdesc[4 * (int64_t)(xo0 + li) + 3];
+        if (w >= 0) { S.ca_tile.push_back(w); w = na++; }
+      }
+      S.ccol3[4 * J + 1] = na;
+      S.max_a_col = std::max(S.max_a_col, na);
+    }
+    // consumers of the "late" update: tile (I, J) feeds target (I, J + 1) together with tile (J + 1, J)
+    S.cnext.assign(n_items_total, -1);
+    S.chas.assign(S.ntc, 0);
+    for (int J = 0; J + 1 < S.ntc; ++J) {
+      const int32_t cp0 = S.col_ptr[J], ncol = S.col_ptr[J + 1] - cp0, xo0 = S.xo_ptr[J];
+      if (ncol < 2 || S.row_idx[cp0 + 1] != J + 1) continue;
+      S.chas[J] = 1;
+      const int32_t np0 = S.col_ptr[J + 1], nncol = S.col_ptr[J + 2] - np0;
+      for (int li = 1; li < ncol; ++li) {
+        const int I = S.row_idx[cp0 + li];
+        const int32_t* b = S.row_idx.data() + np0;
+        const int32_t* e = b + nncol;
+        const int32_t* it = std::lower_bound(b, e, I);
+        if (it != e && *it == I) S.cnext[xo0 + li] = (int32_t)(it - b);
+      }
+      S.cnext[xo0 + ncol] = nncol;     // rhs row feeds the rhs row of the next column
+    }
+    S.ccol.assign(4 * (int64_t)(S.ntc + 1), 0);
+    for (int J = 0; J <= S.ntc; ++J) {
+      S.ccol[4 * J] = S.col_ptr[J];
+      S.ccol[4 * J + 1] = (J < S.ntc) ? S.col_ptr[J + 1] - S.col_ptr[J] : 0;
+      S.ccol[4 * J + 2] = S.xo_ptr[J];
+      S.ccol[4 * J + 3] = (J < S.ntc) ? S.chas[J] : 0;
+    }
+  }
   // flops per mu: 2 * 512 per pair on L targets (8x8x8 multiply-add), plus potrf / trsm ~ 2 * 512 per tile
   S.flops = 0;
   for (int64_t tgt = 0; tgt < n_tiles; ++tgt) S.flops += (int64_t)count[tgt] * 1024;
@@ -172,6 +291,9 @@ int lrbms_symbolic_info(lrbms_symbolic_t s, int32_t what, int64_t* out) {
     case 5: *out = s->n_pairs(); break;
     case 6: *out = s->flops; break;
     case 7: *out = s->max_targets; break;
+    case 8: *out = s->n_win_slots; break;
+    case 9: *out = s->max_col_pairs; break;
+    case 10: *out = s->max_a_col; break;
     default: return LRBMS_ERR_INVALID;
   }
   return LRBMS_OK;
@@ -187,6 +309,15 @@ int64_t lrbms_symbolic_get(lrbms_symbolic_t s, int32_t which, int32_t* out, int6
     case 3: v = &s->pair_a; break;
     case 4: v = &s->pair_b; break;
     case 5: v = &s->a_map; break;
+    case 6: v = &s->win_slot; break;
+    case 7: v = &s->late_ptr; break;
+    case 8: v = &s->win_a; break;
+    case 9: v = &s->win_b; break;
+    case 10: v = &s->xo_ptr; break;
+    case 11: v = &s->xo_idx; break;
+    case 12: v = &s->cnext; break;
+    case 13: v = &s->chas; break;
+    case 14: v = &s->cord; break;
     default: return LRBMS_ERR_INVALID;
   }
   const int64_t n = std::min<int64_t>(cap, (int64_t)v->size());

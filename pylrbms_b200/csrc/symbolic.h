@@ -23,6 +23,32 @@ struct lrbms_symbolic {
   std::vector<int32_t> block_i, block_j;
   int64_t flops = 0;
   int32_t max_targets = 0;
+  // ---- schedule of the shared-memory-window kernel (solve_kernel_v2)
+  // An off-diagonal tile (I, K) of L is live from the step that creates it (column K) until column I has been
+  // formed; live tiles are kept in a shared-memory window.  win_slot[tile] is its window slot (-1: diagonal tile).
+  std::vector<int32_t> win_slot;
+  int32_t n_win_slots = 0;
+  // pairs of every target are sorted by source column K; the "late" pairs (K == J - 1, operands produced by the
+  // immediately preceding column) start at late_ptr[target]
+  std::vector<int32_t> late_ptr;
+  // pair operands as window slots: win_a[p] (or -(K + 1) for the forward-solve row y_K), win_b[p]
+  std::vector<int32_t> win_a, win_b;
+  // targets of each tile column (tiles of the column, then its rhs target) ordered by decreasing early work
+  std::vector<int32_t> xo_ptr, xo_idx;
+  // per-column staging tables of the kernel (indexed xo_ptr[J] + li, li = position of the target in its column,
+  // the rhs target last):  cdesc = {pair begin, late begin, pair end (all relative to the column's staged pair
+  // list), a_map};  cslot = window slot;  cord = li in hand-out order;  cinfo[J] = {first tile pair, tile pairs,
+  // first rhs pair, rhs pairs};  win_ab = interleaved (win_a, win_b)
+  //   cord = li in hand-out order (longest early update first);  cnext = li of the target (I, J + 1) fed by tile (I, J) (-1: none);
+  //   chas[J] = 1 if tile (J + 1, J) exists (then every tile of column J has exactly one "late" consumer in column J + 1)
+  std::vector<int32_t> cdesc, cslot, cord, cinfo, win_ab, cnext, chas;
+  // per-column table kept in shared memory for the whole kernel: ccol[J] = {first tile, tiles, first item, chas[J]}
+  // (one extra entry at J = ntc with the end offsets);  ccol2[J] = {first tile pair, tile pairs, first rhs pair, rhs pairs};
+  // ccol3[J] = {first staged operator tile (index into ca_tile), staged operator tiles, 0, 0};  ca_tile = operator tile
+  // indices (a_map values) in staging order; cdesc[.].w is the staged position of the item's operator tile or -1
+  std::vector<int32_t> ccol, ccol3, ca_tile;
+  int32_t max_a_col = 0;
+  int32_t max_col_pairs = 0;
 
   int64_t n_tiles() const { return (int64_t)row_idx.size(); }
   int64_t n_pairs() const { return (int64_t)pair_a.size(); }

@@ -125,3 +125,29 @@ def test_symbolic_schedule_replays_to_cholesky(built_library, sx, sy, sizes):
     y = np.concatenate([L[n_tiles + J][0] for J in range(ntc)])
     assert np.allclose(Ld @ y, fp, rtol=0, atol=1e-12 * np.abs(fp).max())
     assert sym.flops > 0 and sym.max_targets >= 2
+    # ---- shared-memory window schedule of solve_kernel_v2
+    win_slot, late_ptr, win_a, win_b, xo_ptr, xo_idx = (sym.get(k) for k in range(6, 12))
+    n_slots = sym.n_win_slots
+    # a tile (I, K) is written after column K has been formed and last read while column I is formed; two tiles whose
+    # lifetimes [K, I] overlap must not share a slot (column K's tiles are written after tiles of row K were last read)
+    owner_until = {}
+    for J in range(ntc):
+        for p in range(col_ptr[J], col_ptr[J + 1]):
+            if row_idx[p] == J:
+                assert win_slot[p] == -1
+                continue
+            s_ = win_slot[p]
+            assert 0 <= s_ < n_slots
+            assert owner_until.get(s_, -1) <= J, 'slot {} reused while still live'.format(s_)
+            owner_until[s_] = row_idx[p]
+    for J in range(ntc):
+        items = xo_idx[xo_ptr[J]:xo_ptr[J + 1]]
+        assert sorted(items) == list(range(col_ptr[J], col_ptr[J + 1])) + [n_tiles + J]
+        early = [late_ptr[t_] - pair_ptr[t_] for t_ in items]
+        assert early == sorted(early, reverse=True)
+        for t_ in items:
+            lim = col_ptr[J - 1] if J >= 1 else 0
+            for p in range(pair_ptr[t_], pair_ptr[t_ + 1]):
+                assert (pair_b[p] >= lim) == (p >= late_ptr[t_]) or J == 0
+                assert win_b[p] == win_slot[pair_b[p]]
+                assert win_a[p] == (win_slot[pair_a[p]] if pair_a[p] < n_tiles else -(pair_a[p] - n_tiles + 1))

@@ -363,7 +363,13 @@ def _run_sweep(handle, plan, sysd, theta, with_est):
     (4, 4, [20] * 16),
     (8, 8, [20] * 64),                               # C2 reduced-system shape
 ])
-def test_online_solve_matches_dense(handle, sx, sy, sizes):
+@pytest.mark.parametrize('force_v1', [False, True])
+def test_online_solve_matches_dense(handle, sx, sy, sizes, force_v1, monkeypatch):
+    """Both solve kernels: v2 (shared-memory window, the default when the window fits) and v1 (global scratch)."""
+    if force_v1:
+        monkeypatch.setenv('LRBMS_SOLVE_V1', '1')
+    else:
+        monkeypatch.delenv('LRBMS_SOLVE_V1', raising=False)
     rng = np.random.default_rng(10 + sx * 7 + sy)
     sysd = _random_reduced_system(rng, sx, sy, sizes)
     plan, _ = _make_online_plan(handle, sysd)
