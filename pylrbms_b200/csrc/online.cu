@@ -273,7 +273,7 @@ solve_kernel(SolveParams P, int64_t n_mu, const double* __restrict__ theta, doub
 constexpr int kV2Threads = 512;
 constexpr int kV2Warps = kV2Threads / 32;
 constexpr int kBackStages = 6;     // backward-substitution ring; columns are prefetched kBackStages - 2 ahead
-constexpr int kMetaBufs = 4;     // column metadata is staged two columns ahead (cp.async), four buffers in flight
+constexpr int kMetaBufs = 5;     // column metadata: columns J-1 .. J+3 are alive at the same time (staged by cp.async)
 constexpr int kABufs = 3;        // staged operator tiles: only needed while a column's early updates run
 
 struct SolveParamsV2 {
@@ -345,11 +345,10 @@ solve_kernel_v2(SolveParamsV2 P2, int64_t n_mu, const double* __restrict__ theta
   extern __shared__ __align__(16) double smem[];
   const int MT = P2.max_targets;
   double* win = smem;                                         // region_doubles
-  double* acc0 = win + P2.region_doubles;                     // MT * 64
-  double* acc1 = acc0 + MT * 64;
-  double* sx = acc1 + MT * 64;                                // n_pad
-  double* sW = sx + P.n_pad;                                  // 64
-  double* sred = sW + 64;                                     // 2 * kV2Warps * 8
+  double* acc0 = win + P2.region_doubles;                     // 3 * MT * 64: target sums of columns J-1, J, J+1
+  double* sx = acc0 + 3 * MT * 64;                            // n_pad
+  double* sW = sx + P.n_pad;                                  // 2 * 64: L_JJ^{-1} of the current and the previous column
+  double* sred = sW + 2 * 64;                                 // 2 * kV2Warps * 8
   double* sth = sred + 2 * kV2Warps * 8;                      // n_theta (<= 32)
   double* sA = sth + 32;                                      // kABufs * max_a_col * Q * 64
   const int a_buf_doubles = P2.max_a_col * P.Q * 64;
@@ -406,181 +405,222 @@ solve_kernel_v2(SolveParamsV2 P2, int64_t n_mu, const double* __restrict__ theta
     }
     cp_async_commit();
   };
-  constexpr int kProducer = kV2Warps - 1;
+  constexpr int kProducer = kV2Warps - 1;   // warp 15 only stages data; warp 0 only runs the critical chain
+  constexpr int kUpd = kV2Warps - 2;        // update warps 1..14
+  const bool is_upd = warp > 0 && warp < kProducer;
+
+  // ---- building blocks of the column pipeline -----------------------------------------------------------------
+  // early updates of column Jx (source columns <= Jx - 2) by the 15 update warps -> accX
+  auto early_updates = [&](int Jx, double* accX) {
+    const int mb = Jx % kMetaBufs;
+    const int4* descC = sDesc + mb * MT;
+    const int2* pairC = sPair + mb * P2.max_col_pairs;
+    const int* ordC = sOrd + mb * MT;
+    const double* aC = sA + (Jx % kABufs) * a_buf_doubles;
+    const int ncol = sCol[Jx].y;
+    // Snake deal over the 14 update warps (1..14), longest item first.  Warps 4, 8, 12 share their scheduler (and its
+    // FP64 pipe) with warp 0, which runs the latency-critical diagonal factorisation at the same time: they come last
+    // in every round.
+    const int q4 = warp >> 2;
+    const int posU = (warp & 3) ? (warp - 1 - q4) : (10 + q4);        // 1,2,3,5,6,7,9,10,11,13,14 -> 0..10; 4,8,12 -> 11..13
+    const int posR = (warp & 3) ? (10 - posU) : (14 - q4);            // reverse round: 14,13,11,... -> 0..10; 12,8,4 -> 11..13
+    for (int r = 0; kUpd * r <= ncol; ++r) {
+      const int item = kUpd * r + ((r & 1) ? posR : posU);
+      if (item > ncol) continue;
+      const int li = ordC[item];
+      const int4 d = descC[li];
+      double2 v0 = make_double2(0.0, 0.0), v1 = v0;           // rhs row: loads issued first, consumed last
+      if (li == ncol && g == 0) {
+        v0 = __ldg(reinterpret_cast<const double2*>(P.rhs + 8 * Jx + 2 * t));
+        if (P.Qf > 1) v1 = __ldg(reinterpret_cast<const double2*>(P.rhs + P.n_pad + 8 * Jx + 2 * t));
+      }
+      double acc[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] = 0.0;
+      if (li < ncol) apply_pairs<false>(pairC, win, sx, d.x, d.y, lane, acc);
+      else apply_pairs<true>(pairC, win, sx, d.x, d.y, lane, acc);
+      double a0 = 0.0, a1 = 0.0;
+      if (li < ncol) {
+        if (d.w >= 0) {                                        // A(mu) tile = sum_q theta_q A_q, left to right
+          const double* at = aC + d.w * P.Q * 64 + g * 8 + 2 * t;
+          for (int q = 0; q < P.Q; ++q) {
+            const double2 v = *reinterpret_cast<const double2*>(at + q * 64);
+            if (q == 0) { a0 = sth[0] * v.x; a1 = sth[0] * v.y; }
+            else { a0 += sth[q] * v.x; a1 += sth[q] * v.y; }
+          }
+        }
+      } else {
+        a0 = sth[P.Q] * v0.x; a1 = sth[P.Q] * v0.y;
+        if (P.Qf > 1) { a0 += sth[P.Q + 1] * v1.x; a1 += sth[P.Q + 1] * v1.y; }
+        for (int q = 2; q < P.Qf && g == 0; ++q) {
+          const double2 v = __ldg(reinterpret_cast<const double2*>(P.rhs + (int64_t)q * P.n_pad + 8 * Jx + 2 * t));
+          a0 += sth[P.Q + q] * v.x; a1 += sth[P.Q + q] * v.y;
+        }
+      }
+      *reinterpret_cast<double2*>(accX + li * 64 + lane * 2) =
+          make_double2(a0 + ((acc[0] + acc[4]) + (acc[2] + acc[6])), a1 + ((acc[1] + acc[5]) + (acc[3] + acc[7])));
+    }
+  };
+
+  // column Jy: triangular solve L_IJ = C_IJ L_JJ^{-T} of its off-diagonal tiles and its rhs row (update warps), fused
+  // with the "late" update of column Jy + 1: target (I, Jy+1) -= L_{I,Jy} L_{Jy+1,Jy}^T, done by the warp that just formed
+  // L_{I,Jy}.  The late update of the *diagonal* target belongs to warp 0's critical chain and is skipped here.
+  auto solve_column = [&](int Jy, const double* accY, double* accL, const double* sWy) {
+    const int4 col = sCol[Jy];
+    const int cp0 = col.x, ncol = col.y;
+    const int has_next = (Jy + 1 < P.ntc) ? col.w : 0;
+    const int mbp = Jy % kMetaBufs;
+    const int* slotP = sSlot + mbp * MT;
+    const int* nextP = sNext + mbp * MT;
+    double2 fbn = make_double2(0.0, 0.0);
+    // Slot 0: L_{Jy+1,Jy} (every warp forms it itself instead of waiting for another warp); slots 1, 2: two of this
+    // warp's own items.  The three solves are independent, written side by side so their latencies overlap.
+    for (int base = warp; base <= ncol; base += 2 * kUpd) {
+      const int li[3] = {1, base, base + kUpd};
+      const bool on[3] = {has_next != 0 && base == warp, true, base + kUpd <= ncol};
+      double2 c[3], cc[3];
+      int nl[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        c[k] = on[k] ? *reinterpret_cast<const double2*>(accY + li[k] * 64 + lane * 2) : make_double2(0.0, 0.0);
+        nl[k] = (k > 0 && on[k] && has_next) ? nextP[li[k]] : -1;
+        if (nl[k] == 0) nl[k] = -1;                            // diagonal target: warp 0 does it
+        cc[k] = (nl[k] > 0) ? *reinterpret_cast<const double2*>(accL + nl[k] * 64 + lane * 2) : make_double2(0.0, 0.0);
+      }
+      double x0[3] = {0.0, 0.0, 0.0}, x1[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+      for (int kk = 0; kk < 2; ++kk) {
+        const int src = (lane & ~3) | (2 * kk + (t >> 1));
+        const double b = sWy[g * 8 + 4 * kk + t];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const double v0 = __shfl_sync(0xffffffffu, c[k].x, src);
+          const double v1 = __shfl_sync(0xffffffffu, c[k].y, src);
+          dmma884(x0[k], x1[k], (t & 1) ? v1 : v0, b);
+        }
+      }
+      double2 frag[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) frag[k] = acc_to_frag(lane, x0[k], x1[k]);
+      if (base == warp) fbn = frag[0];
+#pragma unroll
+      for (int k = 1; k < 3; ++k) {
+        if (!on[k]) continue;
+        if (li[k] < ncol) {
+          *reinterpret_cast<double2*>(win + slotP[li[k]] * 64 + lane * 2) = frag[k];
+          *reinterpret_cast<double2*>(L + (int64_t)(cp0 + li[k]) * 64 + lane * 2) = frag[k];
+        } else if (g == 0) {
+          sx[8 * Jy + 2 * t] = x0[k];
+          sx[8 * Jy + 2 * t + 1] = x1[k];
+        }
+        if (nl[k] > 0) {
+          double n0 = 0.0, n1 = 0.0;
+          dmma884(cc[k].x, cc[k].y, -frag[k].x, fbn.x);
+          dmma884(n0, n1, -frag[k].y, fbn.y);
+          *reinterpret_cast<double2*>(accL + nl[k] * 64 + lane * 2) = make_double2(cc[k].x + n0, cc[k].y + n1);
+        }
+      }
+    }
+  };
+
+  // warp 0's critical chain for column Jc: finish the diagonal target (late update with L_{Jc,Jc-1}), then factor it by
+  // row operations on [A | I] held one row per lane, so L^{-1} falls out of the same eight steps -> sWc, and the diagonal
+  // slot of the stored factor
+  auto diagonal_chain = [&](int Jc, const double* accPrev, double* accCur, const double* sWp, double* sWc) {
+    if (Jc >= 1 && sCol[Jc - 1].w) {
+      const double2 c = *reinterpret_cast<const double2*>(accPrev + 64 + lane * 2);      // target (Jc, Jc-1)
+      double x0, x1;
+      apply_inverse_transpose(sWp, lane, c.x, c.y, x0, x1);
+      const double2 frag = acc_to_frag(lane, x0, x1);
+      double2 cc = *reinterpret_cast<const double2*>(accCur + lane * 2);
+      double n0 = 0.0, n1 = 0.0;
+      dmma884(cc.x, cc.y, -frag.x, frag.x);
+      dmma884(n0, n1, -frag.y, frag.y);
+      *reinterpret_cast<double2*>(accCur + lane * 2) = make_double2(cc.x + n0, cc.y + n1);
+      __syncwarp();
+    }
+    // Scalar Cholesky of the 8x8 tile, done redundantly by every lane in registers (packed lower triangle): no
+    // cross-lane traffic on this chain -- shuffles would queue behind the shared-memory traffic of the update warps.
+    double l[36], rinv[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j <= i; ++j) l[i * (i + 1) / 2 + j] = accCur[i * 8 + j];
+    int bad = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      double akk = l[k * (k + 1) / 2 + k];
+      if (8 * Jc + k >= P.n_red) akk = 1.0;                  // padding rows: identity
+      if (!(akk > 0.0)) { if (!bad) bad = 8 * Jc + k + 1; akk = 1.0; }
+      const double r = rsqrt(akk);
+      rinv[k] = r;
+#pragma unroll
+      for (int i = k + 1; i < 8; ++i) l[i * (i + 1) / 2 + k] *= r;
+#pragma unroll
+      for (int j = k + 1; j < 8; ++j)
+#pragma unroll
+        for (int i = j; i < 8; ++i) l[i * (i + 1) / 2 + j] -= l[i * (i + 1) / 2 + k] * l[j * (j + 1) / 2 + k];
+    }
+    if (bad && lane == 0 && s_info == 0) s_info = bad;
+    // column c = lane & 7 of W = L^{-1} by forward substitution (entries above the diagonal come out as exact zeros)
+    const int c = lane & 7;
+    double w[8];
+#pragma unroll
+    for (int ii = 0; ii < 8; ++ii) {
+      double sacc = (ii == c) ? 1.0 : 0.0;
+#pragma unroll
+      for (int k = 0; k < ii; ++k) sacc -= l[ii * (ii + 1) / 2 + k] * w[k];
+      w[ii] = sacc * rinv[ii];
+    }
+    if (lane < 8) {
+      const int64_t dslot = (int64_t)sCol[Jc].x * 64;
+#pragma unroll
+      for (int ii = 0; ii < 8; ++ii) {
+        sWc[ii * 8 + c] = w[ii];
+        L[dslot + ii * 8 + c] = w[ii];                        // the diagonal slot of the stored factor holds L_JJ^{-1}
+      }
+    }
+  };
 
   for (int64_t mu = blockIdx.x; mu < n_mu; mu += gridDim.x) {
     __syncthreads();
     for (int q = threadIdx.x; q < P.n_theta; q += kV2Threads) sth[q] = theta[mu * P.n_theta + q];
     if (threadIdx.x == 0) s_info = 0;
-    if (warp == kProducer) { stage_meta(0); stage_meta(1); }
+    if (warp == kProducer) { stage_meta(0); stage_meta(1); stage_meta(2); }
     cp_async_wait<0>();
     __syncthreads();
-    double* accC = acc0;
-    double* accP = acc1;
     if (timing) tlast = clock64();
+    if (is_upd) early_updates(0, acc0);
+    __syncthreads();
 
-    for (int J = 0; J <= P.ntc; ++J) {
-      if (warp == kProducer) stage_meta(J + 2);
+    // Column pipeline.  Iteration J:  warp 0 runs the critical chain of column J (late update of the diagonal target,
+    // factorisation, inverse) while the update warps solve column J-1 against L_{J-1,J-1}^{-1}, apply the late updates of
+    // column J, synchronise among themselves and accumulate the early updates of column J+1.
+    for (int J = 0; J < P.ntc; ++J) {
+      if (warp == kProducer) stage_meta(J + 3);
       LRBMS_TICK(0);
-      const int mb = J % kMetaBufs, mbp = (J + kMetaBufs - 1) % kMetaBufs;
-      const int4* descC = sDesc + mb * MT;
-      const int2* pairC = sPair + mb * P2.max_col_pairs;
-      const int4 colC = sCol[J];                                   // (J == ntc: empty column)
-      const int4 colP = sCol[J > 0 ? J - 1 : 0];
-      const int has_next = (J >= 1 && J < P.ntc) ? colP.w : 0;
-      double2 fbn_keep = make_double2(0.0, 0.0);
-      // ---------------- diagonal tile of column J-1 (warp 0): Cholesky by row operations on [A | I] held one row per
-      //                  lane, so L^{-1} (what the triangular solves multiply with) falls out of the same eight steps
-      if (warp == 0 && J >= 1) {
-        const int Jp = J - 1;
-        const int i = lane & 7;
-        double a[8], w[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { a[j] = accP[i * 8 + j]; w[j] = (j == i) ? 1.0 : 0.0; }
-        int bad = 0;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          double akk = __shfl_sync(0xffffffffu, a[k], k);
-          if (8 * Jp + k >= P.n_red) akk = 1.0;                  // padding rows: identity
-          if (!(akk > 0.0)) { if (!bad) bad = 8 * Jp + k + 1; akk = 1.0; }
-          const double r = rsqrt(akk);
-          const double lik = ((i == k) ? akk : a[k]) * r;        // L[i][k] for i >= k
-          a[k] = lik;
-          double pj[8], wj[8];
-#pragma unroll
-          for (int j = k + 1; j < 8; ++j) pj[j] = __shfl_sync(0xffffffffu, lik, j);      // L[j][k]
-#pragma unroll
-          for (int j = 0; j <= k; ++j) wj[j] = __shfl_sync(0xffffffffu, w[j], k) * r;    // scaled pivot row of W
-          if (i > k) {
-#pragma unroll
-            for (int j = k + 1; j < 8; ++j) a[j] -= lik * pj[j];
-#pragma unroll
-            for (int j = 0; j <= k; ++j) w[j] -= lik * wj[j];
-          } else if (i == k) {
-#pragma unroll
-            for (int j = 0; j <= k; ++j) w[j] = wj[j];
-          }
-        }
-        if (bad && lane == 0 && s_info == 0) s_info = bad;
-        if (lane < 8) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const double v = (j <= i) ? w[j] : 0.0;
-            sW[i * 8 + j] = v;
-            L[(int64_t)colP.x * 64 + i * 8 + j] = v;           // the diagonal slot of the stored factor holds L_JJ^{-1}
-          }
-        }
+      double* accPrev = acc0 + ((J + 2) % 3) * MT * 64;       // target sums of column J-1 (pointer arithmetic on purpose:
+      double* accCur = acc0 + (J % 3) * MT * 64;              // an indexed pointer array would live in local memory)
+      double* accNext = acc0 + ((J + 1) % 3) * MT * 64;
+      double* sWprev = sW + ((J + 1) & 1) * 64;
+      double* sWcur = sW + (J & 1) * 64;
+      if (warp == 0) {
+        diagonal_chain(J, accPrev, accCur, sWprev, sWcur);
+        LRBMS_TICK(1);
+      } else if (is_upd) {
+        if (J >= 1) solve_column(J - 1, accPrev, accCur, sWprev);
+        LRBMS_TICK(1);
+        asm volatile("bar.sync 1, %0;\n" ::"n"(kUpd * 32) : "memory");   // column J-1 of L visible to the update warps
+        LRBMS_TICK(2);
+        if (J + 1 < P.ntc) early_updates(J + 1, accNext);
+        LRBMS_TICK(3);
       }
-      LRBMS_TICK(1);
-      // ---------------- early updates of column J (source columns <= J-2), dealt to the 15 update warps
-      if (J < P.ntc && warp > 0) {
-        const int ncol = colC.y;
-        const int* ordC = sOrd + mb * MT;
-        const double* aC = sA + (J % kABufs) * a_buf_doubles;
-        // snake deal (warp 0 is busy with the diagonal tile): round r hands items 15 r .. 15 r + 14 to warps 1..15
-        // (r even) or 15..1 (r odd), longest items first
-        for (int r = 0; 15 * r <= ncol; ++r) {
-          const int item = 15 * r + ((r & 1) ? (15 - warp) : (warp - 1));
-          if (item > ncol) break;
-          const int li = ordC[item];
-          const int4 d = descC[li];
-          double2 v0 = make_double2(0.0, 0.0), v1 = v0;           // rhs row: loads issued first, consumed last
-          if (li == ncol && g == 0) {
-            v0 = __ldg(reinterpret_cast<const double2*>(P.rhs + 8 * J + 2 * t));
-            if (P.Qf > 1) v1 = __ldg(reinterpret_cast<const double2*>(P.rhs + P.n_pad + 8 * J + 2 * t));
-          }
-          double acc[8];
-#pragma unroll
-          for (int k = 0; k < 8; ++k) acc[k] = 0.0;
-          if (li < ncol) apply_pairs<false>(pairC, win, sx, d.x, d.y, lane, acc);
-          else apply_pairs<true>(pairC, win, sx, d.x, d.y, lane, acc);
-          double a0 = 0.0, a1 = 0.0;
-          if (li < ncol) {
-            if (d.w >= 0) {                                        // A(mu) tile = sum_q theta_q A_q, left to right
-              const double* at = aC + d.w * P.Q * 64 + g * 8 + 2 * t;
-              for (int q = 0; q < P.Q; ++q) {
-                const double2 v = *reinterpret_cast<const double2*>(at + q * 64);
-                if (q == 0) { a0 = sth[0] * v.x; a1 = sth[0] * v.y; }
-                else { a0 += sth[q] * v.x; a1 += sth[q] * v.y; }
-              }
-            }
-          } else {
-            a0 = sth[P.Q] * v0.x; a1 = sth[P.Q] * v0.y;
-            if (P.Qf > 1) { a0 += sth[P.Q + 1] * v1.x; a1 += sth[P.Q + 1] * v1.y; }
-            for (int q = 2; q < P.Qf && g == 0; ++q) {
-              const double2 v = __ldg(reinterpret_cast<const double2*>(P.rhs + (int64_t)q * P.n_pad + 8 * J + 2 * t));
-              a0 += sth[P.Q + q] * v.x; a1 += sth[P.Q + q] * v.y;
-            }
-          }
-          *reinterpret_cast<double2*>(accC + li * 64 + lane * 2) =
-              make_double2(a0 + ((acc[0] + acc[4]) + (acc[2] + acc[6])), a1 + ((acc[1] + acc[5]) + (acc[3] + acc[7])));
-        }
-      }
-      LRBMS_TICK(2);
-      __syncthreads();   // B1: W_{J-1} ready, early sums of column J stored
-      LRBMS_TICK(3);
-      // ---------------- column J-1: triangular solve L_IJ = C_IJ L_JJ^{-T} (rhs row likewise), fused with the "late"
-      //                  update of column J: target (I, J) -= L_{I,J-1} L_{J,J-1}^T, done by the warp that just formed L_{I,J-1}
-      if (J >= 1) {
-        const int Jp = J - 1;
-        const int cp0 = colP.x, ncol = colP.y;
-        const int* slotP = sSlot + mbp * MT;
-        const int* nextP = sNext + mbp * MT;
-        // Slot 0: L_{J,J-1} (every warp forms it itself instead of waiting for another warp); slots 1, 2: two of this
-        // warp's own items.  The three solves are independent, written side by side so their latencies overlap.
-        for (int base = 1 + warp; base <= ncol || base == 1 + warp; base += 2 * kV2Warps) {
-          int li[3] = {1, base, base + kV2Warps};
-          bool on[3] = {has_next != 0 && base == 1 + warp && base <= ncol, base <= ncol, base + kV2Warps <= ncol};
-          if (!on[0] && !on[1]) break;
-          double2 c[3], cc[3];
-          int nl[3];
-#pragma unroll
-          for (int k = 0; k < 3; ++k) {
-            c[k] = on[k] ? *reinterpret_cast<const double2*>(accP + li[k] * 64 + lane * 2) : make_double2(0.0, 0.0);
-            nl[k] = (k > 0 && on[k] && has_next) ? nextP[li[k]] : -1;
-            cc[k] = (nl[k] >= 0) ? *reinterpret_cast<const double2*>(accC + nl[k] * 64 + lane * 2) : make_double2(0.0, 0.0);
-          }
-          double x0[3] = {0.0, 0.0, 0.0}, x1[3] = {0.0, 0.0, 0.0};
-#pragma unroll
-          for (int kk = 0; kk < 2; ++kk) {
-            const int src = (lane & ~3) | (2 * kk + (t >> 1));
-            const double b = sW[g * 8 + 4 * kk + t];
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-              const double v0 = __shfl_sync(0xffffffffu, c[k].x, src);
-              const double v1 = __shfl_sync(0xffffffffu, c[k].y, src);
-              dmma884(x0[k], x1[k], (t & 1) ? v1 : v0, b);
-            }
-          }
-          double2 frag[3];
-#pragma unroll
-          for (int k = 0; k < 3; ++k) frag[k] = acc_to_frag(lane, x0[k], x1[k]);
-          if (base == 1 + warp) fbn_keep = frag[0];
-#pragma unroll
-          for (int k = 1; k < 3; ++k) {
-            if (!on[k]) continue;
-            if (li[k] < ncol) {
-              *reinterpret_cast<double2*>(win + slotP[li[k]] * 64 + lane * 2) = frag[k];
-              *reinterpret_cast<double2*>(L + (int64_t)(cp0 + li[k]) * 64 + lane * 2) = frag[k];
-            } else if (g == 0) {
-              sx[8 * Jp + 2 * t] = x0[k];
-              sx[8 * Jp + 2 * t + 1] = x1[k];
-            }
-            if (nl[k] >= 0) {
-              double n0 = 0.0, n1 = 0.0;
-              dmma884(cc[k].x, cc[k].y, -frag[k].x, fbn_keep.x);
-              dmma884(n0, n1, -frag[k].y, fbn_keep.y);
-              *reinterpret_cast<double2*>(accC + nl[k] * 64 + lane * 2) = make_double2(cc[k].x + n0, cc[k].y + n1);
-            }
-          }
-        }
-      }
+      cp_async_wait<1>();   // everything staged for column J+2 has landed (column J+3 may still be in flight)
+      __syncthreads();
       LRBMS_TICK(4);
-      cp_async_wait<1>();   // everything staged for column J+1 has landed (column J+2 may still be in flight)
-      __syncthreads();      // B2: column J-1 of L, y_{J-1} and the completed targets of column J visible
-      LRBMS_TICK(5);
-      double* tmp = accC; accC = accP; accP = tmp;
     }
+    if (is_upd) solve_column(P.ntc - 1, acc0 + ((P.ntc - 1) % 3) * MT * 64, acc0 + (P.ntc % 3) * MT * 64, sW + ((P.ntc - 1) & 1) * 64);
+    LRBMS_TICK(5);
     cp_async_wait<0>();
 
     // ---------------- backward substitution  L^T u = y: the factor streams back through a cp.async ring; one
@@ -970,7 +1010,7 @@ int lrbms_online_plan_create(lrbms_handle_t h, const lrbms_reduced_system_t* sys
     const int MT = S.max_targets;
     const int64_t region = std::max<int64_t>((int64_t)S.n_win_slots * 64, (int64_t)kBackStages * maxcol * 64);
     const int mcp = std::max(1, S.max_col_pairs), mac = std::max(1, S.max_a_col);
-    const size_t bytes = sizeof(double) * ((size_t)region + 2 * (size_t)MT * 64 + S.n_pad + 64 + 2 * kV2Warps * 8 + 32 +
+    const size_t bytes = sizeof(double) * ((size_t)region + 3 * (size_t)MT * 64 + S.n_pad + 2 * 64 + 2 * kV2Warps * 8 + 32 +
                                            (size_t)kABufs * mac * Q * 64) +
                          16 * ((size_t)kMetaBufs * MT + (size_t)(S.ntc + 1) + 2 * (size_t)S.ntc) + 8 * (size_t)kMetaBufs * mcp +
                          4 * (3 * (size_t)kMetaBufs * MT + S.ca_tile.size()) + 64;

@@ -15,8 +15,8 @@ plan=rd.online_plan
 out=np.zeros(128,dtype=np.int64)
 n=plan.handle.lib.lrbms_online_debug_timing(plan.p, out.ctypes.data, 128)
 t=out.reshape(16,8)/8.0   # per mu (8 mu per CTA)
-names=['meta','potrf','X','B1','Y','B2','back','store']
+names=['meta','chain|Y','ubar','X','endbar','epi','back','store']
 print('cycles per mu, per warp:')
 print('warp '+' '.join('%9s'%n for n in names)+'   total')
 for w in range(16): print('%4d '%w+' '.join('%9.0f'%v for v in t[w])+'  %9.0f'%t[w].sum())
-print('per column (161 iterations): ', ' '.join('%s=%.0f'%(n, t[:,k].mean()/161) for k,n in enumerate(names[:6])))
+print('per column: ', ' '.join('%s=%.0f'%(n, t[1:,k].mean()/160) for k,n in enumerate(names[:6])), ' warp0 chain=%.0f'%(t[0,1]/160))
