@@ -697,10 +697,11 @@ solve_kernel_v2(SolveParamsV2 P2, int64_t n_mu, const double* __restrict__ theta
 // ------------------------------------------------------------------------------------------------------
 //  estimator
 // ------------------------------------------------------------------------------------------------------
-constexpr int kEstThreads = 256;
+constexpr int kEstThreads = 512;
 constexpr int kEstWarps = kEstThreads / 32;
-constexpr int kTMU = 32;         // parameters per CTA
-constexpr int kLDX = 36;         // shared row stride (doubles): 36 mod 16 == 4 -> conflict-free DMMA fragment loads
+constexpr int kTMU = 64;         // parameters per CTA: every estimator matrix is read once per 64 parameters
+constexpr int kLDX = 68;         // shared row stride (doubles): 68 mod 16 == 4 -> conflict-free DMMA fragment loads
+constexpr int kMaxEstTerms = 64; // terms per subdomain
 
 struct DevTerm {
   const double* M;
@@ -719,7 +720,7 @@ struct EstParams {
   const double* r_scale;
 };
 
-__global__ void __launch_bounds__(kEstThreads)
+__global__ void __launch_bounds__(kEstThreads, 1)
 estimate_kernel(EstParams P, int64_t n_mu, const double* __restrict__ theta, const double* __restrict__ u,
                 double* __restrict__ parts) {
   extern __shared__ double smem[];
@@ -727,6 +728,7 @@ estimate_kernel(EstParams P, int64_t n_mu, const double* __restrict__ theta, con
   double* XR = XN + (int64_t)P.dmax_pad * kLDX;        // qdmax_pad x kLDX
   double* TH = XR + (int64_t)P.qdmax_pad * kLDX;       // Q x kTMU
   double* OUTW = TH + P.Q * kTMU;                      // kEstWarps x 3 x kTMU
+  __shared__ int s_tile_ptr[kMaxEstTerms + 1];         // row tiles (8 rows) of the subdomain's terms, prefix sums
 
   const int sub = blockIdx.y;
   const int64_t mu0 = (int64_t)blockIdx.x * kTMU;
@@ -740,6 +742,12 @@ estimate_kernel(EstParams P, int64_t n_mu, const double* __restrict__ theta, con
     TH[i] = (m < nmu) ? theta[(mu0 + m) * P.n_theta + q] : 0.0;
   }
   for (int i = threadIdx.x; i < kEstWarps * 3 * kTMU; i += kEstThreads) OUTW[i] = 0.0;
+  const int t0 = P.term_ptr[sub], n_terms = P.term_ptr[sub + 1] - t0;
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int k = 0; k < n_terms; ++k) { s_tile_ptr[k] = acc; acc += (P.terms[t0 + k].rows + 7) >> 3; }
+    s_tile_ptr[n_terms] = acc;
+  }
   const int nb0 = P.nbh_ptr[sub], nb1 = P.nbh_ptr[sub + 1];
   int d = 0, lo_self = 0;
   for (int e = nb0; e < nb1; ++e) {
@@ -772,56 +780,52 @@ estimate_kernel(EstParams P, int64_t n_mu, const double* __restrict__ theta, con
   }
   __syncthreads();
 
-  // ---- terms
-  for (int ti = P.term_ptr[sub]; ti < P.term_ptr[sub + 1]; ++ti) {
-    const DevTerm T = P.terms[ti];
+  // ---- (term, 8-row tile) work items dealt round-robin to the warps: Y = M X on DMMA, then the column dot with X_L
+  const int n_tiles = s_tile_ptr[n_terms];
+  int ti = 0;
+  for (int idx = warp; idx < n_tiles; idx += kEstWarps) {
+    while (s_tile_ptr[ti + 1] <= idx) ++ti;
+    const DevTerm T = P.terms[t0 + ti];
+    const int r0 = 8 * (idx - s_tile_ptr[ti]);
     const double* XRt = (T.right_kind == LRBMS_VEC_UR) ? XR : (T.right_kind == LRBMS_VEC_UN ? XN : XN + lo_self * kLDX);
     const double* XLt = (T.left_kind == LRBMS_VEC_UR) ? XR : (T.left_kind == LRBMS_VEC_UN ? XN : XN + lo_self * kLDX);
     const int kend = (T.cols + 3) & ~3;
-    double ps[kTMU / 8][2];
+    double acc[kTMU / 8][2];
 #pragma unroll
-    for (int n = 0; n < kTMU / 8; ++n) ps[n][0] = ps[n][1] = 0.0;
-    for (int r0 = 8 * warp; r0 < T.rows; r0 += 8 * kEstWarps) {
-      double acc[kTMU / 8][2];
+    for (int n = 0; n < kTMU / 8; ++n) acc[n][0] = acc[n][1] = 0.0;
+    const bool rok = r0 + g < T.rows;
+    const double* __restrict__ Mr = T.M + (int64_t)(r0 + g) * T.cols;
+#pragma unroll 2
+    for (int k0 = 0; k0 < kend; k0 += 4) {
+      const double a = (rok && k0 + t < T.cols) ? __ldg(Mr + k0 + t) : 0.0;
+      const double* xb = XRt + (k0 + t) * kLDX + g;
 #pragma unroll
-      for (int n = 0; n < kTMU / 8; ++n) acc[n][0] = acc[n][1] = 0.0;
-      const bool rok = r0 + g < T.rows;
-      const double* __restrict__ Mr = T.M + (int64_t)(r0 + g) * T.cols;
-      for (int k0 = 0; k0 < kend; k0 += 4) {
-        const double a = (rok && k0 + t < T.cols) ? __ldg(Mr + k0 + t) : 0.0;
-        const double* xb = XRt + (k0 + t) * kLDX + g;
+      for (int n = 0; n < kTMU / 8; ++n) dmma884(acc[n][0], acc[n][1], a, xb[8 * n]);
+    }
+    // column dot with the left vector (rows r0 + g, parameters 8n + 2t, 8n + 2t + 1), reduced over the 8 rows of the
+    // tile (lanes with equal t), scaled, accumulated in this warp's private slice
 #pragma unroll
-        for (int n = 0; n < kTMU / 8; ++n) dmma884(acc[n][0], acc[n][1], a, xb[8 * n]);
+    for (int n = 0; n < kTMU / 8; ++n) {
+      double l0 = 0.0, l1 = 0.0;
+      if (rok) {
+        if (T.left_kind == LRBMS_VEC_ONE) { l0 = 1.0; l1 = 1.0; }
+        else { l0 = XLt[(r0 + g) * kLDX + 8 * n + 2 * t]; l1 = XLt[(r0 + g) * kLDX + 8 * n + 2 * t + 1]; }
       }
-      // column dot with the left vector: rows r0 + g, parameters 8n + 2t, 8n + 2t + 1
+      double v0 = l0 * acc[n][0], v1 = l1 * acc[n][1];
 #pragma unroll
-      for (int n = 0; n < kTMU / 8; ++n) {
-        double l0 = 0.0, l1 = 0.0;
-        if (rok) {
-          if (T.left_kind == LRBMS_VEC_ONE) { l0 = 1.0; l1 = 1.0; }
-          else { l0 = XLt[(r0 + g) * kLDX + 8 * n + 2 * t]; l1 = XLt[(r0 + g) * kLDX + 8 * n + 2 * t + 1]; }
-        }
-        ps[n][0] += l0 * acc[n][0];
-        ps[n][1] += l1 * acc[n][1];
+      for (int o = 4; o < 32; o <<= 1) {
+        v0 += __shfl_xor_sync(0xffffffffu, v0, o);
+        v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+      }
+      if (g == 0) {
+        const int m = 8 * n + 2 * t;
+        double cf0 = T.coef, cf1 = T.coef;
+        if (T.qa >= 0) { cf0 *= TH[T.qa * kTMU + m]; cf1 *= TH[T.qa * kTMU + m + 1]; }
+        if (T.qb >= 0) { cf0 *= TH[T.qb * kTMU + m]; cf1 *= TH[T.qb * kTMU + m + 1]; }
+        OUTW[(warp * 3 + T.out_kind) * kTMU + m] += cf0 * v0;
+        OUTW[(warp * 3 + T.out_kind) * kTMU + m + 1] += cf1 * v1;
       }
     }
-    // reduce over the 8 rows of the tile (lanes with equal t), scale, accumulate in this warp's private slice
-#pragma unroll
-    for (int n = 0; n < kTMU / 8; ++n)
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        double v = ps[n][j];
-        v += __shfl_xor_sync(0xffffffffu, v, 4);
-        v += __shfl_xor_sync(0xffffffffu, v, 8);
-        v += __shfl_xor_sync(0xffffffffu, v, 16);
-        if (g == 0) {
-          const int m = 8 * n + 2 * t + j;
-          double cf = T.coef;
-          if (T.qa >= 0) cf *= TH[T.qa * kTMU + m];
-          if (T.qb >= 0) cf *= TH[T.qb * kTMU + m];
-          OUTW[(warp * 3 + T.out_kind) * kTMU + m] += cf * v;
-        }
-      }
     __syncwarp();
   }
   __syncthreads();
@@ -1094,6 +1098,10 @@ int lrbms_online_plan_create(lrbms_handle_t h, const lrbms_reduced_system_t* sys
     std::vector<DevTerm> terms;
     double est_flops = 0;
     for (int i = 0; i < S.n_sub; ++i) {
+      if ((int)per_sub[i].size() > kMaxEstTerms) {
+        lrbms_plan_destroy(P);
+        return lrbms_fail(h, LRBMS_ERR_UNSUPPORTED, "online_plan_create: more than 64 estimator terms on one subdomain");
+      }
       for (const DevTerm& D : per_sub[i]) { terms.push_back(D); est_flops += 2.0 * D.rows * D.cols; }
       term_ptr[i + 1] = (int32_t)terms.size();
     }
