@@ -120,6 +120,9 @@ typedef struct {
   double* out;             /* device, row-major NL x NR: out[a * ldo + b] (overwritten) */
   int32_t ldo;
   double alpha;
+  int32_t symmetric;       /* caller asserts A = A^T and VL, VR are the same array: only the lower-triangular output
+                              chunks are computed and mirrored (estimator Grams nc_i, r_dd_i, df_bb_i, products) */
+  int32_t reserved;
 } lrbms_project_desc_t;
 
 int lrbms_project_plan_create(lrbms_handle_t h, int32_t n_desc, const lrbms_project_desc_t* descs_host,

@@ -45,7 +45,7 @@ class ProjectDesc(C.Structure):
                 ('VL', C.c_void_p), ('ldl', C.c_int32), ('NL', C.c_int32),
                 ('VR', C.c_void_p), ('ldr', C.c_int32), ('NR', C.c_int32),
                 ('out', C.c_void_p), ('ldo', C.c_int32),
-                ('alpha', C.c_double)]
+                ('alpha', C.c_double), ('symmetric', C.c_int32), ('reserved', C.c_int32)]
 
 
 class EstimatorTerm(C.Structure):

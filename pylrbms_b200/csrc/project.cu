@@ -29,6 +29,7 @@ struct ProjItem {
   int32_t group;      // output group (desc, l-chunk, r-chunk)
   int32_t slot;       // index of this item inside its group
   int32_t group_size;
+  int32_t mirror;     // symmetric descriptor, off-diagonal chunk pair: also write the transposed chunk
 };
 
 struct DevDesc {       // device-side mirror of lrbms_project_desc_t (VR/rowptr possibly redirected to scratch)
@@ -62,13 +63,13 @@ project_kernel(const ProjItem* __restrict__ items, const DevDesc* __restrict__ d
   const double* __restrict__ VL = D.VL + it.l0 + g;
   const double* __restrict__ VR = D.VR + it.c0 + g;
 
-  for (int k0 = it.row0 + 4 * warp; k0 < it.row1; k0 += 4 * kWarps) {
-    const int row = k0 + t;
-    const bool row_ok = row < it.row1;
-    double b[NT];
+  if (HAS_A) {
+    for (int k0 = it.row0 + 4 * warp; k0 < it.row1; k0 += 4 * kWarps) {
+      const int row = k0 + t;
+      const bool row_ok = row < it.row1;
+      double b[NT];
 #pragma unroll
-    for (int n = 0; n < NT; ++n) b[n] = 0.0;
-    if (HAS_A) {
+      for (int n = 0; n < NT; ++n) b[n] = 0.0;
       int p0 = 0, len = 0;
       if (row_ok) {
         p0 = D.rowptr[row];
@@ -88,28 +89,52 @@ project_kernel(const ProjItem* __restrict__ items, const DevDesc* __restrict__ d
             if (8 * n + g < nr) b[n] = fma(a, vr[8 * n], b[n]);
         }
       }
-    } else {
+      any_work = true;
+      double a[MT];
+#pragma unroll
+      for (int m = 0; m < MT; ++m) a[m] = 0.0;
       if (row_ok) {
-        const double* __restrict__ vr = VR + (int64_t)row * D.ldr;
+        const double* __restrict__ vl = VL + (int64_t)row * D.ldl;
 #pragma unroll
-        for (int n = 0; n < NT; ++n)
-          if (8 * n + g < nr) b[n] = vr[8 * n];
+        for (int m = 0; m < MT; ++m)
+          if (8 * m + g < nl) a[m] = vl[8 * m];
       }
-    }
-    any_work = true;
-    double a[MT];
-#pragma unroll
-    for (int m = 0; m < MT; ++m) a[m] = 0.0;
-    if (row_ok) {
-      const double* __restrict__ vl = VL + (int64_t)row * D.ldl;
 #pragma unroll
       for (int m = 0; m < MT; ++m)
-        if (8 * m + g < nl) a[m] = vl[8 * m];
+#pragma unroll
+        for (int n = 0; n < NT; ++n) dmma884(acc[m][n][0], acc[m][n][1], a[m], b[n]);
     }
+  } else {
+    // dense G = VL^T VR: register double buffering -- the fragments of the next k-step are in flight while the
+    // MT x NT DMMAs of the current one issue
+    auto load_frags = [&](int k0, double (&a)[MT], double (&b)[NT]) {
+      const int row = k0 + t;
+      const bool row_ok = row < it.row1;
+      const double* __restrict__ vl = VL + (int64_t)row * D.ldl;
+      const double* __restrict__ vr = VR + (int64_t)row * D.ldr;
 #pragma unroll
-    for (int m = 0; m < MT; ++m)
+      for (int m = 0; m < MT; ++m) a[m] = (row_ok && 8 * m + g < nl) ? vl[8 * m] : 0.0;
 #pragma unroll
-      for (int n = 0; n < NT; ++n) dmma884(acc[m][n][0], acc[m][n][1], a[m], b[n]);
+      for (int n = 0; n < NT; ++n) b[n] = (row_ok && 8 * n + g < nr) ? vr[8 * n] : 0.0;
+    };
+    int k0 = it.row0 + 4 * warp;
+    if (k0 < it.row1) {
+      any_work = true;
+      double a_cur[MT], b_cur[NT], a_nxt[MT], b_nxt[NT];
+      load_frags(k0, a_cur, b_cur);
+      for (; k0 < it.row1; k0 += 4 * kWarps) {
+        const int k1 = k0 + 4 * kWarps;
+        if (k1 < it.row1) load_frags(k1, a_nxt, b_nxt);
+#pragma unroll
+        for (int m = 0; m < MT; ++m)
+#pragma unroll
+          for (int n = 0; n < NT; ++n) dmma884(acc[m][n][0], acc[m][n][1], a_cur[m], b_cur[n]);
+#pragma unroll
+        for (int m = 0; m < MT; ++m) a_cur[m] = a_nxt[m];
+#pragma unroll
+        for (int n = 0; n < NT; ++n) b_cur[n] = b_nxt[n];
+      }
+    }
   }
 
   // ---- reduce the 8 warps in fixed order through shared memory
@@ -137,7 +162,9 @@ project_kernel(const ProjItem* __restrict__ items, const DevDesc* __restrict__ d
   if (it.group_size == 1) {
     for (int e = threadIdx.x; e < nl * nr; e += kThreads) {
       const int a = e / nr, bb = e - a * nr;
-      D.out[(int64_t)(it.l0 + a) * D.ldo + it.c0 + bb] = D.alpha * red[((a >> 3) * NT + (bb >> 3)) * 64 + (a & 7) * 8 + (bb & 7)];
+      const double v = D.alpha * red[((a >> 3) * NT + (bb >> 3)) * 64 + (a & 7) * 8 + (bb & 7)];
+      D.out[(int64_t)(it.l0 + a) * D.ldo + it.c0 + bb] = v;
+      if (it.mirror) D.out[(int64_t)(it.c0 + bb) * D.ldo + it.l0 + a] = v;
     }
     return;
   }
@@ -163,6 +190,7 @@ project_kernel(const ProjItem* __restrict__ items, const DevDesc* __restrict__ d
     for (int sl = 0; sl < it.group_size; ++sl)
       if (__ldcg(&flags[base + sl])) s += __ldcg(&partials[(base + sl) * kPartialStride + idx]);
     D.out[(int64_t)(it.l0 + a) * D.ldo + it.c0 + bb] = D.alpha * s;
+    if (it.mirror) D.out[(int64_t)(it.c0 + bb) * D.ldo + it.l0 + a] = D.alpha * s;
   }
   __syncthreads();
   if (threadIdx.x == 0) counters[it.group] = 0;   // self-cleaning for the next run
@@ -494,9 +522,11 @@ int lrbms_project_plan_create(lrbms_handle_t h, int32_t n_desc, const lrbms_proj
     const int n_lch = (x.NL + 8 * kMaxTile - 1) / (8 * kMaxTile), n_rch = (x.NR + 8 * kMaxTile - 1) / (8 * kMaxTile);
     // balanced chunk widths (e.g. 100 -> 3 chunks of 40, 32, 32 is worse than 3 x 5 tiles, 4, 4): use tiles
     const int lt = (x.NL + 7) / 8, rt = (x.NR + 7) / 8;
+    const bool symmetric = descs_host[i].symmetric != 0 && x.NL == x.NR;
     for (int lc = 0; lc < n_lch; ++lc) {
       const int lt0 = (int)((int64_t)lt * lc / n_lch), lt1 = (int)((int64_t)lt * (lc + 1) / n_lch);
       for (int rc_ = 0; rc_ < n_rch; ++rc_) {
+        if (symmetric && rc_ > lc) continue;          // upper chunks are mirrored from the lower ones
         const int rt0 = (int)((int64_t)rt * rc_ / n_rch), rt1 = (int)((int64_t)rt * (rc_ + 1) / n_rch);
         const int mt = lt1 - lt0, nt = rt1 - rt0;
         const int n_split = (int)std::max<int64_t>(1, (x.n_rows + rows_per_cta - 1) / rows_per_cta);
@@ -511,6 +541,7 @@ int lrbms_project_plan_create(lrbms_handle_t h, int32_t n_desc, const lrbms_proj
           it.desc = i; it.l0 = 8 * lt0; it.c0 = 8 * rt0;
           it.row0 = (int32_t)r0; it.row1 = (int32_t)std::min<int64_t>(x.n_rows, r0 + std::max<int64_t>(4, rows_each));
           it.group = group; it.slot = slot++; it.group_size = 0;
+          it.mirror = (symmetric && rc_ != lc) ? 1 : 0;
           bucket.push_back(it);
         }
         for (size_t k = first; k < bucket.size(); ++k) bucket[k].group_size = slot;

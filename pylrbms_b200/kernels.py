@@ -35,6 +35,7 @@ class DeviceCsr:
         self.values = torch.from_numpy(np.ascontiguousarray(M.data if M.nnz else np.zeros(1), dtype=np.float64)).cuda()
         self._host = M
         self._T = None
+        self._symmetric = None
 
     @property
     def host(self):
@@ -49,6 +50,20 @@ class DeviceCsr:
         return self._T
 
     @property
+    def symmetric(self):
+        """True if the matrix equals its transpose up to rounding of the assembly (checked once, on the host copy)."""
+        if self._symmetric is None:
+            M = self._host
+            if M.shape[0] != M.shape[1]:
+                self._symmetric = False
+            elif M.nnz == 0:
+                self._symmetric = True
+            else:
+                D = abs(M - M.T)
+                self._symmetric = bool(D.max() <= 1e-13 * abs(M).max())
+        return self._symmetric
+
+    @property
     def device_bytes(self):
         return 4 * (self.shape[0] + 1) + 12 * self.nnz
 
@@ -58,13 +73,15 @@ def spmm_desc(csr, V_ptr, ldv, N, W_ptr, ldw):
                     V_ptr, ldv, N, W_ptr, ldw)
 
 
-def project_desc(csr, n_rows, VL_ptr, ldl, NL, VR_ptr, ldr, NR, out_ptr, ldo, alpha=1.0):
-    """``csr=None`` selects the identity operator (Gram matrix ``VL^T VR``)."""
+def project_desc(csr, n_rows, VL_ptr, ldl, NL, VR_ptr, ldr, NR, out_ptr, ldo, alpha=1.0, symmetric=False):
+    """``csr=None`` selects the identity operator (Gram matrix ``VL^T VR``).  ``symmetric=True`` asserts that the
+    operator is symmetric and ``VL`` / ``VR`` are the same array (only the lower output chunks are computed)."""
+    sym = 1 if (symmetric and VL_ptr == VR_ptr and ldl == ldr and NL == NR) else 0
     if csr is None:
-        return ProjectDesc(None, None, None, n_rows, n_rows, VL_ptr, ldl, NL, VR_ptr, ldr, NR, out_ptr, ldo, float(alpha))
+        return ProjectDesc(None, None, None, n_rows, n_rows, VL_ptr, ldl, NL, VR_ptr, ldr, NR, out_ptr, ldo, float(alpha), sym, 0)
     assert csr.shape[0] == n_rows
     return ProjectDesc(csr.rowptr.data_ptr(), csr.colind.data_ptr(), csr.values.data_ptr(), csr.shape[0], csr.shape[1],
-                       VL_ptr, ldl, NL, VR_ptr, ldr, NR, out_ptr, ldo, float(alpha))
+                       VL_ptr, ldl, NL, VR_ptr, ldr, NR, out_ptr, ldo, float(alpha), sym, 0)
 
 
 def spmm_once(csr, V, range_space):

@@ -194,7 +194,8 @@ class _Planner:
         token = self.alloc(owner, L.N * R.N)
         if L.N and R.N and self.mine(owner):
             n_rows = csr.shape[0] if csr is not None else L.dim
-            self.jobs.append((token, csr, n_rows, L, R, R.N, alpha))
+            sym = (L.ptr == R.ptr and L.ld == R.ld and L.N == R.N and L.N > 40 and (csr is None or csr.symmetric))
+            self.jobs.append((token, csr, n_rows, L, R, R.N, alpha, sym))
         self.keep += [csr, L.keep, R.keep]
         return token
 
@@ -206,9 +207,9 @@ class _Planner:
         self.out = torch.zeros(max(1, int(starts[-1])), dtype=torch.float64, device='cuda')
         base = self.out.data_ptr()
         descs = []
-        for (token, csr, n_rows, L, R, ldo, alpha) in self.jobs:
+        for (token, csr, n_rows, L, R, ldo, alpha, sym) in self.jobs:
             descs.append(project_desc(csr, n_rows, L.ptr, L.ld, L.N, R.ptr, R.ld, R.N, base + 8 * int(self.offsets[token]),
-                                      ldo, alpha))
+                                      ldo, alpha, symmetric=sym))
         self.spmm_plans = [make_spmm_plan(self.h, st, []) for st in self.spmm_stages if st]
         self.project_plan = make_project_plan(self.h, descs, []) if descs else None
         self.n_project_descs = len(descs)

@@ -224,6 +224,44 @@ def test_project_batched(handle):
     assert plan.algorithmic_bytes > 0 and plan.algorithmic_bytes_survey >= plan.algorithmic_bytes * 0.5
 
 
+def test_project_symmetric_flag(handle):
+    """``symmetric = 1``: only the lower output chunks are computed, the upper ones are mirrored (exactly symmetric)."""
+    from pylrbms_b200._lib import make_project_plan, ProjectDesc
+    torch = _torch()
+    rng = np.random.default_rng(4)
+    n, N = 3000, 100
+    B = random_csr(rng, n, n, 4)
+    A = sp.csr_matrix(B + B.T)
+    A.sort_indices()
+    dA = DevCsr(A)
+    V = dofmajor(rng, n, N)
+    dV = dev(V)
+    outs = []
+    for sym in (0, 1):
+        out = torch.full((N, N), np.nan, dtype=torch.float64, device='cuda')
+        d = ProjectDesc(dA.rowptr.data_ptr(), dA.colind.data_ptr(), dA.values.data_ptr(), n, n, dV.data_ptr(), N, N,
+                        dV.data_ptr(), N, N, out.data_ptr(), N, 1.0, sym, 0)
+        plan = make_project_plan(handle, [d], [dA, dV, out])
+        plan.run()
+        torch.cuda.synchronize()
+        outs.append(out.cpu().numpy())
+    ref = V.T @ (A @ V)
+    scale = np.abs(V).T @ np.abs(A @ V)
+    for got in outs:
+        assert (np.abs(got - ref) / scale).max() < 1e-13
+    # off-diagonal output chunks are mirrored exactly, diagonal chunks are symmetric up to rounding
+    assert np.array_equal(outs[1][64:, :32], outs[1][:32, 64:].T)
+    assert (np.abs(outs[1] - outs[1].T) / scale).max() < 1e-13
+    # identity operator (plain Gram matrix), symmetric
+    out = torch.full((N, N), np.nan, dtype=torch.float64, device='cuda')
+    d = ProjectDesc(None, None, None, n, n, dV.data_ptr(), N, N, dV.data_ptr(), N, N, out.data_ptr(), N, 1.0, 1, 0)
+    plan = make_project_plan(handle, [d], [dV, out])
+    plan.run()
+    torch.cuda.synchronize()
+    got = out.cpu().numpy()
+    assert np.abs(got - V.T @ V).max() < 1e-10 and np.array_equal(got[64:, :32], got[:32, 64:].T)
+
+
 def test_project_all_zero_operator(handle):
     """An operator without any stored entry projects to exact zeros (no NaN from untouched scratch)."""
     from pylrbms_b200._lib import make_project_plan, ProjectDesc
