@@ -242,6 +242,10 @@ def _gather_columns(planner, arrays):
     """Concatenate dof-major arrays column-wise.  Zero-copy when they already are adjacent column slices of one
     slab (which is how ``LRBMSReductor`` lays out the OI / RT image bases); otherwise one device copy."""
     arrays = list(arrays)
+    nonempty = [a for a in arrays if len(a) > 0]          # empty bases contribute no columns (and have no address)
+    if not nonempty:
+        return _ArrayRef.of(arrays[0])
+    arrays = nonempty
     if len(arrays) == 1:
         return _ArrayRef.of(arrays[0])
     adjacent = all(a.ld == arrays[0].ld for a in arrays) and all(
@@ -249,6 +253,9 @@ def _gather_columns(planner, arrays):
     total = sum(len(a) for a in arrays)
     if adjacent:
         return _ArrayRef(arrays[0].device_ptr, arrays[0].ld, total, arrays[0].dim, arrays)
+    if any(getattr(a, '_is_view', False) for a in arrays):
+        # slab views are filled by the plan's first SpMM stage, i.e. after planning: copying them now would copy zeros
+        raise NotImplementedError('image bases of one neighbourhood must be adjacent column slices of one slab')
     cat = GpuVectorArray(arrays[0].space, None, total)
     pos = 0
     for a in arrays:

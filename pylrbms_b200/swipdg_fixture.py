@@ -677,7 +677,7 @@ def make_local_bases(data: BlockSwipdgData, basis_size, seed=0, noise=0.05):
             v = np.cos(np.pi * k * xi[:, 0]) * np.cos(np.pi * l * xi[:, 1])
             v = v + noise * rng.standard_normal(v.shape) * np.abs(v).max()
             cand.append(v)
-        V = np.array(cand[:N])
+        V = np.array(cand[:N]).reshape(N, int(data.n[i]))
         E = data.energy[i]
         for _ in range(2):
             for a in range(N):

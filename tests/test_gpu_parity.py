@@ -213,3 +213,57 @@ def test_vectorarray_interface(handle):
     assert np.array_equal(a[2:4].data, A[2:4])
     z = sp_.zeros(3)
     assert z.is_zero() and not a.is_zero() and z.data.shape == (3, 1000)
+
+
+def test_empty_local_bases(handle):
+    """Subdomains without any basis function (an empty ``bases['domain_k']``, the state before the first enrichment of a
+    subdomain) contribute zero-sized blocks; everything else must still match the oracle."""
+    from pylrbms_b200.swipdg_fixture import assemble_block_swipdg, make_local_bases
+    from pylrbms_b200 import discretize, LRBMSReductor
+    from oracle import lrbms_oracle as O
+    data = assemble_block_swipdg((3, 2), 4)
+    bases = make_local_bases(data, [3, 0, 4, 5, 0, 2], seed=2)
+    bd = {'domain_%d' % i: bases[i] for i in range(6)}
+    rd_ref = O.LRBMSReductor(O.build_discretization(data), bases=bd).reduce()
+    rd = LRBMSReductor(discretize(data)[0], bases=bd).reduce()
+    assert rd.block_dims == [3, 0, 4, 5, 0, 2] and rd.n_red == 14
+    for q in range(2):
+        A, B = rd.operator.operators[q].to_dense(), rd_ref.operator.operators[q].matrix
+        assert A.shape == B.shape == (14, 14) and np.abs(A - B).max() <= RTOL * np.abs(B).max()
+    mus = np.array([0.2, 0.9])
+    U, eta, parts, ind = rd.sweep(mus, decompose=True)
+    for k, mu in enumerate(mus):
+        U_ref = rd_ref.solve(mu)
+        eta_ref, parts_ref, _ = rd_ref.estimate(U_ref, mu, decompose=True)
+        assert np.abs(U.data[k] - U_ref.data[0]).max() <= 1e-9 * np.abs(U_ref.data).max()
+        assert abs(eta[k] - eta_ref) <= RTOL * abs(eta_ref)
+        assert np.abs(parts[0][:, k] - parts_ref[0][:, 0]).max() <= RTOL * max(np.abs(parts_ref[0]).max(), 1e-300)
+
+
+def test_error_behaviour(handle):
+    """Errors surface as exceptions carrying the library's message (C ABI: negative status + lrbms_last_error); a reduced
+    operator that is not positive definite is reported, not silently 'solved'."""
+    import ctypes as C
+    from pylrbms_b200 import LrbmsError
+    from pylrbms_b200._lib import ProjectDesc, make_project_plan, ptr, current_stream_ptr
+    with pytest.raises(LrbmsError, match='null pointer'):
+        make_project_plan(handle, [ProjectDesc(None, None, None, 4, 4, None, 1, 1, None, 1, 1, None, 1, 1.0, 0, 0)])
+    with pytest.raises(LrbmsError, match='inconsistent sizes'):
+        import torch
+        t = torch.zeros(16, dtype=torch.float64, device='cuda')
+        make_project_plan(handle, [ProjectDesc(None, None, None, 4, 4, t.data_ptr(), 1, 2, t.data_ptr(), 1, 2, t.data_ptr(), 2, 1.0, 0, 0)])
+    data, d_ref, red_ref, d, red = _setup((2, 2), 4, 4, 9)
+    rd = red.reduce()
+    with pytest.raises(LrbmsError, match='not positive definite'):
+        rd.solve(50.0)                       # lambda = 1 + (1 - mu) cos(..)cos(..) < 0 in the interior: indefinite
+    with pytest.raises(ValueError):
+        rd.estimate_batch(rd.solve_batch([0.5, 0.6]), [0.5])          # one solution per parameter
+    # workspace too small is rejected by the library
+    import torch
+    plan = rd.online_plan
+    theta = torch.from_numpy(rd.thetas([0.5])).cuda()
+    u = torch.zeros((1, rd.n_red), dtype=torch.float64, device='cuda')
+    info = torch.zeros(1, dtype=torch.int32, device='cuda')
+    w = torch.zeros(64, dtype=torch.uint8, device='cuda')
+    rc = plan.handle.lib.lrbms_online_solve(plan.p, 1, ptr(theta), ptr(u), ptr(info), ptr(w), 64, current_stream_ptr())
+    assert rc == -1 and b'workspace too small' in plan.handle.lib.lrbms_last_error(plan.handle.h)
