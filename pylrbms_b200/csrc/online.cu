@@ -348,7 +348,8 @@ solve_kernel_v2(SolveParamsV2 P2, int64_t n_mu, const double* __restrict__ theta
   double* acc0 = win + P2.region_doubles;                     // 3 * MT * 64: target sums of columns J-1, J, J+1
   double* sx = acc0 + 3 * MT * 64;                            // n_pad
   double* sW = sx + P.n_pad;                                  // 2 * 64: L_JJ^{-1} of the current and the previous column
-  double* sred = sW + 2 * 64;                                 // 2 * kV2Warps * 8
+  double* sScr = sW + 2 * 64;                                 // 2 * 64: layout-conversion scratch (shared tile, chain warp)
+  double* sred = sScr + 2 * 64;                               // 2 * kV2Warps * 8
   double* sth = sred + 2 * kV2Warps * 8;                      // n_theta (<= 32)
   double* sA = sth + 32;                                      // kABufs * max_a_col * Q * 64
   const int a_buf_doubles = P2.max_a_col * P.Q * 64;
@@ -478,30 +479,40 @@ solve_kernel_v2(SolveParamsV2 P2, int64_t n_mu, const double* __restrict__ theta
     for (int base = warp; base <= ncol; base += 2 * kUpd) {
       const int li[3] = {1, base, base + kUpd};
       const bool on[3] = {has_next != 0 && base == warp, true, base + kUpd <= ncol};
-      double2 c[3], cc[3];
+      // X = C W^T.  C is read from its row-major accumulator tile directly in DMMA A-fragment order and X goes back
+      // through shared memory to reach the operand-fragment order -- no shuffles (they queue behind the LDS traffic).
+      double x0[3] = {0.0, 0.0, 0.0}, x1[3] = {0.0, 0.0, 0.0};
+      double a0[3], a1[3];
+      double2 cc[3];
       int nl[3];
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
-        c[k] = on[k] ? *reinterpret_cast<const double2*>(accY + li[k] * 64 + lane * 2) : make_double2(0.0, 0.0);
+        const double* ct = accY + li[k] * 64 + g * 8 + t;
+        a0[k] = on[k] ? ct[0] : 0.0;
+        a1[k] = on[k] ? ct[4] : 0.0;
         nl[k] = (k > 0 && on[k] && has_next) ? nextP[li[k]] : -1;
         if (nl[k] == 0) nl[k] = -1;                            // diagonal target: warp 0 does it
         cc[k] = (nl[k] > 0) ? *reinterpret_cast<const double2*>(accL + nl[k] * 64 + lane * 2) : make_double2(0.0, 0.0);
       }
-      double x0[3] = {0.0, 0.0, 0.0}, x1[3] = {0.0, 0.0, 0.0};
+      const double b0 = sWy[g * 8 + t], b1 = sWy[g * 8 + 4 + t];
 #pragma unroll
-      for (int kk = 0; kk < 2; ++kk) {
-        const int src = (lane & ~3) | (2 * kk + (t >> 1));
-        const double b = sWy[g * 8 + 4 * kk + t];
+      for (int k = 0; k < 3; ++k) dmma884(x0[k], x1[k], a0[k], b0);
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          const double v0 = __shfl_sync(0xffffffffu, c[k].x, src);
-          const double v1 = __shfl_sync(0xffffffffu, c[k].y, src);
-          dmma884(x0[k], x1[k], (t & 1) ? v1 : v0, b);
-        }
+      for (int k = 0; k < 3; ++k) dmma884(x0[k], x1[k], a1[k], b1);
+      __syncwarp();                                            // all lanes have read their C fragments
+      double* tile[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        // own tiles are dead after this solve and serve as scratch; the shared tile (1) is read by every warp, so its
+        // result goes to a common scratch tile (all warps write identical values)
+        tile[k] = (li[k] == 1) ? sScr : const_cast<double*>(accY) + li[k] * 64;
+        if (on[k]) *reinterpret_cast<double2*>(tile[k] + lane * 2) = make_double2(x0[k], x1[k]);
       }
+      __syncwarp();
       double2 frag[3];
 #pragma unroll
-      for (int k = 0; k < 3; ++k) frag[k] = acc_to_frag(lane, x0[k], x1[k]);
+      for (int k = 0; k < 3; ++k)
+        frag[k] = on[k] ? make_double2(tile[k][g * 8 + t], tile[k][g * 8 + t + 4]) : make_double2(0.0, 0.0);
       if (base == warp) fbn = frag[0];
 #pragma unroll
       for (int k = 1; k < 3; ++k) {
@@ -528,10 +539,14 @@ solve_kernel_v2(SolveParamsV2 P2, int64_t n_mu, const double* __restrict__ theta
   // slot of the stored factor
   auto diagonal_chain = [&](int Jc, const double* accPrev, double* accCur, const double* sWp, double* sWc) {
     if (Jc >= 1 && sCol[Jc - 1].w) {
-      const double2 c = *reinterpret_cast<const double2*>(accPrev + 64 + lane * 2);      // target (Jc, Jc-1)
-      double x0, x1;
-      apply_inverse_transpose(sWp, lane, c.x, c.y, x0, x1);
-      const double2 frag = acc_to_frag(lane, x0, x1);
+      const double* ct = accPrev + 64 + g * 8 + t;                                       // target (Jc, Jc-1)
+      double x0 = 0.0, x1 = 0.0;
+      dmma884(x0, x1, ct[0], sWp[g * 8 + t]);
+      dmma884(x0, x1, ct[4], sWp[g * 8 + 4 + t]);
+      double* scr = sScr + 64;
+      *reinterpret_cast<double2*>(scr + lane * 2) = make_double2(x0, x1);
+      __syncwarp();
+      const double2 frag = make_double2(scr[g * 8 + t], scr[g * 8 + t + 4]);
       double2 cc = *reinterpret_cast<const double2*>(accCur + lane * 2);
       double n0 = 0.0, n1 = 0.0;
       dmma884(cc.x, cc.y, -frag.x, frag.x);
@@ -1014,7 +1029,7 @@ int lrbms_online_plan_create(lrbms_handle_t h, const lrbms_reduced_system_t* sys
     const int MT = S.max_targets;
     const int64_t region = std::max<int64_t>((int64_t)S.n_win_slots * 64, (int64_t)kBackStages * maxcol * 64);
     const int mcp = std::max(1, S.max_col_pairs), mac = std::max(1, S.max_a_col);
-    const size_t bytes = sizeof(double) * ((size_t)region + 3 * (size_t)MT * 64 + S.n_pad + 2 * 64 + 2 * kV2Warps * 8 + 32 +
+    const size_t bytes = sizeof(double) * ((size_t)region + 3 * (size_t)MT * 64 + S.n_pad + 4 * 64 + 2 * kV2Warps * 8 + 32 +
                                            (size_t)kABufs * mac * Q * 64) +
                          16 * ((size_t)kMetaBufs * MT + (size_t)(S.ntc + 1) + 2 * (size_t)S.ntc) + 8 * (size_t)kMetaBufs * mcp +
                          4 * (3 * (size_t)kMetaBufs * MT + S.ca_tile.size()) + 64;
