@@ -37,6 +37,14 @@ sys.path.insert(0, ROOT)
 METRIC = 'online reduced solves+estimates/s (mu-batched)'
 UNIT = 'solves+estimates/s'
 
+# DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed `ncu --set full` captures
+# of the default workload (profiles/r01_final_ncu_full_*_raw.csv); null for any other workload.
+NCU_TRAFFIC_BYTES = {
+    'solve_kernel_v2': 11.743e9 + 16.449e9,           # 10 000 parameters per launch
+    'projection_plan': (0.0755 + 0.5789 + 0.4077 + 1.2004 + 0.2934 + 0.2211 + 2.0698 + 1.3553) * 1e9 +
+                       (0.0030 + 0.0079 + 0.0154 + 0.0188 + 0.0048 + 0.0073 + 0.0917 + 2.4280) * 1e9,   # 7 project + 1 spmm launch
+}
+
 
 # ----------------------------------------------------------------------------------------------------------
 #  workload
@@ -275,6 +283,7 @@ def run_b200(a):
     rd.online_plan                                     # build the online plan (symbolic phase + tile upload)
 
     flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device='cuda')     # 256 MB > 126 MB L2
+    fp64_peak = measure_fp64_gemm_peak(torch)
 
     def flush_l2():
         flush.fill_(1.0)
@@ -308,10 +317,15 @@ def run_b200(a):
             'launches_per_reduce': st['launches'],
             'roofline': {'bound': 'hbm', 'kernel': 'project_kernel (all buckets of one plan run)',
                          'achieved': pp.algorithmic_bytes_survey / t_proj / 1e9, 'peak': hbm_peak, 'unit': 'GB/s',
-                         'frac': pp.algorithmic_bytes_survey / t_proj / 1e9 / hbm_peak, 'traffic': None,
+                         'frac': pp.algorithmic_bytes_survey / t_proj / 1e9 / hbm_peak,
+                         'traffic': NCU_TRAFFIC_BYTES['projection_plan'] if (a.subdomains, a.cells, a.basis) == (8, 32, 20) else None,
                          'peak_source': hbm_src, 'algorithmic_bytes_survey_formula': pp.algorithmic_bytes_survey,
                          'algorithmic_bytes_tight': pp.algorithmic_bytes, 'flops': pp.flops,
-                         'achieved_tflops': pp.flops / t_proj / 1e12},
+                         'achieved_tflops': pp.flops / t_proj / 1e12, 'fp64_peak_tflops': fp64_peak,
+                         'frac_of_fp64_peak': pp.flops / t_proj / 1e12 / fp64_peak,
+                         'note': 'with the estimator Grams the plan has an arithmetic intensity of flops/bytes = %.1f flop/B, '
+                                 'above the HBM/FP64 crossover: the binding roofline is the FP64 tensor pipe' %
+                                 (pp.flops / pp.algorithmic_bytes_survey)},
             'first_reduce_incl_planning_s': t_reduce_first,
         }
 
@@ -385,12 +399,14 @@ def run_b200(a):
 
     # ---- roofline of the dominant kernel (solve_kernel: FP64 tensor-core tile Cholesky)
     fl = survey_flops_per_mu(a.subdomains, a.basis, data.Q)
-    fp64_peak = measure_fp64_gemm_peak(torch)
     solve_s = float(np.mean(t_solve)) * 1e-3
     achieved = fl['solve'] * n_mu / solve_s / 1e12
     from pylrbms_b200._lib import Symbolic
-    roofline = {'bound': 'tensor', 'kernel': 'solve_kernel', 'achieved': achieved, 'peak': fp64_peak, 'unit': 'TFLOP/s',
-                'frac': achieved / fp64_peak, 'traffic': None,
+    default_workload = (a.subdomains, a.cells, a.basis, a.n_mu) == (8, 32, 20, 10000)
+    solve_name = 'solve_kernel_v2' if os.environ.get('LRBMS_SOLVE_V1', '0') in ('', '0') else 'solve_kernel'
+    roofline = {'bound': 'tensor', 'kernel': solve_name, 'achieved': achieved, 'peak': fp64_peak, 'unit': 'TFLOP/s',
+                'frac': achieved / fp64_peak,
+                'traffic': NCU_TRAFFIC_BYTES.get(solve_name) if default_workload else None,
                 'peak_source': 'cuBLAS DGEMM 4096^3 measured in this run (FP64; MEASURED_PEAKS.json has no FP64 figure)',
                 'algorithmic_flops_per_mu': fl['solve'], 'ms_per_launch': 1e3 * solve_s,
                 'share_of_step': float(np.sum(t_solve) / np.sum(t_step))}
