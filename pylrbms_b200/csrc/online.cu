@@ -638,8 +638,10 @@ solve_kernel_v2(SolveParamsV2 P2, int64_t n_mu, const double* __restrict__ theta
     LRBMS_TICK(5);
     cp_async_wait<0>();
 
-    // ---------------- backward substitution  L^T u = y: the factor streams back through a cp.async ring; one
-    //                  barrier per tile column, every warp finishes u_J redundantly from the partial sums
+    // ---------------- backward substitution  L^T u = y.  The factor streams back through a cp.async ring.  Per tile
+    //                  column J (descending): warp 0 finishes u_J -- partial sums of column J (formed one iteration
+    //                  earlier by the other warps), the one contribution that needs u_{J+1}, then L_JJ^{-T} -- while
+    //                  warps 1..15 already form the partial sums of column J-1 from u_I, I >= J+1.  One barrier per column.
     {
       const int stage = P2.back_stage_doubles;
       auto issue = [&](int Jc) {
@@ -647,57 +649,77 @@ solve_kernel_v2(SolveParamsV2 P2, int64_t n_mu, const double* __restrict__ theta
           const int4 col = sCol[Jc];
           double* dst = win + ((P.ntc - 1 - Jc) % kBackStages) * stage;
           const double* src = L + (int64_t)col.x * 64;
-          for (int c = threadIdx.x; c < col.y * 32; c += kV2Threads) cp_async16(dst + 2 * c, src + 2 * c);
-          int* rdst = sSlot + ((P.ntc - 1 - Jc) % kBackStages) * MT;   // sSlot/sOrd/sNext are free now: 12 MT ints
-          if (threadIdx.x < col.y) cp_async4(rdst + threadIdx.x, P.row_idx + col.x + threadIdx.x);
+          // warp 0 runs the serial chain and issues no copies
+          const int tid = (int)threadIdx.x - 32;
+          if (tid >= 0) {
+            for (int c = tid; c < col.y * 32; c += kV2Threads - 32) cp_async16(dst + 2 * c, src + 2 * c);
+            int* rdst = sSlot + ((P.ntc - 1 - Jc) % kBackStages) * MT;   // sSlot/sOrd/sNext are free now: 15 MT ints
+            if (tid < col.y) cp_async4(rdst + tid, P.row_idx + col.x + tid);
+          }
         }
         cp_async_commit();
       };
-      // A ring slot is refilled only two barriers after its last reader: prefetch distance kBackStages - 2
+      for (int i = threadIdx.x; i < 2 * kV2Warps * 8; i += kV2Threads) sred[i] = 0.0;
       for (int s = 0; s < kBackStages - 2; ++s) issue(P.ntc - 1 - s);
-      cp_async_wait<kBackStages - 3>();       // column ntc-1 has landed
+      cp_async_wait<kBackStages - 4>();       // columns ntc-1 and ntc-2 have landed
       __syncthreads();
       for (int J = P.ntc - 1; J >= 0; --J) {
         issue(J - (kBackStages - 2));
-        const int bsel = (P.ntc - 1 - J) % kBackStages;
-        const double* buf = win + bsel * stage;
-        const int* rows = sSlot + bsel * MT;
-        const int ncol = sCol[J].y;
-        double s0 = 0.0, s1 = 0.0;       // partial sums for solution components t and t + 4
-        for (int li = 1 + warp; li < ncol; li += kV2Warps) {
-          const double2 f = *reinterpret_cast<const double2*>(buf + li * 64 + lane * 2);
-          const double xv = sx[8 * rows[li] + g];
-          s0 += f.x * xv;
-          s1 += f.y * xv;
-        }
-#pragma unroll
-        for (int o = 4; o < 32; o <<= 1) {
-          s0 += __shfl_xor_sync(0xffffffffu, s0, o);
-          s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-        }
-        double* red = sred + (J & 1) * kV2Warps * 8;
-        if (g == 0) { red[warp * 8 + t] = s0; red[warp * 8 + 4 + t] = s1; }
-        cp_async_wait<kBackStages - 3>();     // column J-1 has landed (needed right after the barrier)
-        __syncthreads();
-        {
-          // lane (q, c), q = lane >> 3: sums four of the sixteen partials of component c, then a two-step butterfly
+        if (warp == 0) {
+          const int bsel = (P.ntc - 1 - J) % kBackStages;
+          const double* buf = win + bsel * stage;
+          const double* red = sred + (J & 1) * kV2Warps * 8;
           const int cidx = lane & 7, q4 = lane >> 3;
+          // lane (q, c): four of the sixteen partials of component c, then a two-step butterfly
           const double* rq = red + (q4 * 4) * 8 + cidx;
           double part = (rq[0] + rq[8]) + (rq[16] + rq[24]);
           part += __shfl_xor_sync(0xffffffffu, part, 8);
           part += __shfl_xor_sync(0xffffffffu, part, 16);
+          if (sCol[J].w) {                     // tile (J+1, J): the only contribution that needs u_{J+1}
+            const double2 f = *reinterpret_cast<const double2*>(buf + 64 + lane * 2);
+            const double xv = sx[8 * (J + 1) + g];
+            double s0 = f.x * xv, s1 = f.y * xv;     // components t and t + 4, to be summed over g
+#pragma unroll
+            for (int o = 4; o < 32; o <<= 1) {
+              s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+              s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+            }
+            const double v0 = __shfl_sync(0xffffffffu, s0, cidx & 3), v1 = __shfl_sync(0xffffffffu, s1, cidx & 3);
+            part += (cidx < 4) ? v0 : v1;
+          }
           const double v = sx[8 * J + cidx] - part;            // lanes c, c + 8, c + 16, c + 24 all hold v_c
           // u_c = sum_k W[k][c] v_k: lane (q, c) takes k = 2q, 2q + 1
           double accv = buf[(2 * q4) * 8 + cidx] * __shfl_sync(0xffffffffu, v, 2 * q4) +
                         buf[(2 * q4 + 1) * 8 + cidx] * __shfl_sync(0xffffffffu, v, 2 * q4 + 1);
           accv += __shfl_xor_sync(0xffffffffu, accv, 8);
           accv += __shfl_xor_sync(0xffffffffu, accv, 16);
-          if (lane < 8) sx[8 * J + cidx] = accv;     // every warp writes the same values: no second barrier needed
-          __syncwarp();
+          if (lane < 8) sx[8 * J + cidx] = accv;
+        } else {
+          double s0 = 0.0, s1 = 0.0;           // partial sums of column J-1 for solution components t and t + 4
+          if (J >= 1) {
+            const int bsel = (P.ntc - J) % kBackStages;
+            const double* buf = win + bsel * stage;
+            const int* rows = sSlot + bsel * MT;
+            const int4 col = sCol[J - 1];
+            for (int li = 1 + col.w + (warp - 1); li < col.y; li += kV2Warps - 1) {    // skip tile (J, J-1)
+              const double2 f = *reinterpret_cast<const double2*>(buf + li * 64 + lane * 2);
+              const double xv = sx[8 * rows[li] + g];
+              s0 += f.x * xv;
+              s1 += f.y * xv;
+            }
+#pragma unroll
+            for (int o = 4; o < 32; o <<= 1) {
+              s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+              s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+            }
+          }
+          double* red = sred + ((J + 1) & 1) * kV2Warps * 8;   // = ((J - 1) & 1): partials of column J-1
+          if (g == 0) { red[warp * 8 + t] = s0; red[warp * 8 + 4 + t] = s1; }
         }
+        cp_async_wait<kBackStages - 4>();     // columns J-1 and J-2 have landed
+        __syncthreads();
       }
       cp_async_wait<0>();
-      __syncthreads();
     }
     LRBMS_TICK(6);
     for (int i = threadIdx.x; i < P.n_red; i += kV2Threads) u[mu * P.n_red + i] = sx[i];
