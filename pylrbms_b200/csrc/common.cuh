@@ -26,6 +26,7 @@ struct lrbms_plan {
   double info_launches = 0, info_ctas = 0, info_bytes = 0, info_flops = 0, info_bytes_survey = 0;
   virtual ~lrbms_plan() {}
   virtual int run(void* stream) = 0;
+  virtual void ensure_info() {}       // byte / flop accounting is computed on first request, not at plan creation
 };
 
 extern thread_local std::string g_create_error;

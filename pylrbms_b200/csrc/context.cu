@@ -61,6 +61,7 @@ int lrbms_plan_destroy(lrbms_plan_t plan) {
 
 int lrbms_plan_info(lrbms_plan_t plan, int32_t what, double* out) {
   if (!plan || !out) return LRBMS_ERR_INVALID;
+  if (what == 2 || what == 3 || what == 5) plan->ensure_info();
   switch (what) {
     case 0: *out = plan->info_launches; break;
     case 1: *out = plan->info_ctas; break;

@@ -327,7 +327,10 @@ struct ProjectPlan : lrbms_plan {
   // two-step path (large N with a sparse operator): SpMM into plan-owned scratch first
   lrbms_spmm_desc_t* d_spmm_descs = nullptr;
   std::vector<SpmmLaunch> spmm_launches;
+  std::vector<lrbms_project_desc_t> host_descs;
+  bool accounted = false;
   int run(void* stream) override;
+  void ensure_info() override;
 };
 
 template <int MT, int NT, bool HAS_A>
@@ -356,6 +359,42 @@ static void dispatch_mt(const ProjLaunch& L, const ProjectPlan* P, cudaStream_t 
     case 4: dispatch_nt<4, HAS_A>(L, P, s); break;
     default: dispatch_nt<5, HAS_A>(L, P, s); break;
   }
+}
+
+// accounting (tight and SURVEY-formula byte counts) from the device CSR data; lazy because it costs two small kernels
+// and two synchronous copies per descriptor
+void ProjectPlan::ensure_info() {
+  if (accounted) return;
+  accounted = true;
+  unsigned long long* d_cnt = nullptr;
+  unsigned char* d_flag = nullptr;
+  int max_cols = 1;
+  for (const auto& d : host_descs) max_cols = std::max(max_cols, d.n_cols);
+  if (cudaMalloc((void**)&d_cnt, 2 * sizeof(unsigned long long)) != cudaSuccess) return;
+  if (cudaMalloc((void**)&d_flag, (size_t)max_cols) != cudaSuccess) { cudaFree(d_cnt); return; }
+  for (const auto& d : host_descs) {
+    double nl = d.NL, nr = d.NR, r = d.n_rows, c = d.n_cols;
+    if (!d.rowptr) {
+      double b = 8.0 * r * (nl + nr) + 8.0 * nl * nr;
+      info_bytes += b; info_bytes_survey += b; info_flops += 2.0 * r * nl * nr;
+      continue;
+    }
+    int32_t nnz = 0;
+    unsigned long long cnt[2] = {0, 0};
+    if (d.n_rows > 0) {
+      cudaMemcpy(&nnz, d.rowptr + d.n_rows, sizeof(int32_t), cudaMemcpyDeviceToHost);
+      cudaMemset(d_cnt, 0, 2 * sizeof(unsigned long long));
+      cudaMemset(d_flag, 0, (size_t)std::max(1, d.n_cols));
+      csr_stats_kernel<<<64, 256>>>(d.rowptr, d.colind, d.n_rows, d_flag, d_cnt);
+      count_flags_kernel<<<64, 256>>>(d_flag, d.n_cols, d_cnt);
+      cudaMemcpy(cnt, d_cnt, sizeof(cnt), cudaMemcpyDeviceToHost);
+    }
+    info_bytes += 12.0 * nnz + 4.0 * (r + 1) + 8.0 * (double)cnt[1] * nr + 8.0 * (double)cnt[0] * nl + 8.0 * nl * nr;
+    info_bytes_survey += 12.0 * nnz + 4.0 * (r + 1) + 8.0 * c * nr + 8.0 * r * nl + 8.0 * nl * nr;
+    info_flops += 2.0 * nnz * nr + 2.0 * r * nl * nr;
+  }
+  cudaFree(d_cnt);
+  cudaFree(d_flag);
 }
 
 int ProjectPlan::run(void* stream) {
@@ -465,41 +504,7 @@ int lrbms_project_plan_create(lrbms_handle_t h, int32_t n_desc, const lrbms_proj
   }
   if (rc) { lrbms_plan_destroy(P); return rc; }
 
-  // ---- accounting (tight and SURVEY-formula byte counts) from the device CSR data
-  {
-    unsigned long long* d_cnt = nullptr;
-    unsigned char* d_flag = nullptr;
-    int max_cols = 1;
-    for (int i = 0; i < n_desc; ++i) max_cols = std::max(max_cols, descs_host[i].n_cols);
-    cudaMalloc((void**)&d_cnt, 2 * sizeof(unsigned long long));
-    cudaMalloc((void**)&d_flag, (size_t)max_cols);
-    for (int i = 0; i < n_desc; ++i) {
-      const auto& d = descs_host[i];
-      double nl = d.NL, nr = d.NR, r = d.n_rows, c = d.n_cols;
-      if (!d.rowptr) {
-        double b = 8.0 * r * (nl + nr) + 8.0 * nl * nr;
-        P->info_bytes += b; P->info_bytes_survey += b; P->info_flops += 2.0 * r * nl * nr;
-        continue;
-      }
-      int32_t nnz = 0;
-      unsigned long long cnt[2] = {0, 0};
-      if (d.n_rows > 0) {
-        cudaMemcpy(&nnz, d.rowptr + d.n_rows, sizeof(int32_t), cudaMemcpyDeviceToHost);
-        cudaMemset(d_cnt, 0, 2 * sizeof(unsigned long long));
-        cudaMemset(d_flag, 0, (size_t)std::max(1, d.n_cols));
-        csr_stats_kernel<<<64, 256>>>(d.rowptr, d.colind, d.n_rows, d_flag, d_cnt);
-        count_flags_kernel<<<64, 256>>>(d_flag, d.n_cols, d_cnt);
-        cudaMemcpy(cnt, d_cnt, sizeof(cnt), cudaMemcpyDeviceToHost);
-      }
-      P->info_bytes += 12.0 * nnz + 4.0 * (r + 1) + 8.0 * (double)cnt[1] * nr + 8.0 * (double)cnt[0] * nl + 8.0 * nl * nr;
-      P->info_bytes_survey += 12.0 * nnz + 4.0 * (r + 1) + 8.0 * c * nr + 8.0 * r * nl + 8.0 * nl * nr;
-      P->info_flops += 2.0 * nnz * nr + 2.0 * r * nl * nr;
-    }
-    cudaFree(d_cnt);
-    cudaFree(d_flag);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) { lrbms_plan_destroy(P); return lrbms_fail(h, LRBMS_ERR_CUDA, cudaGetErrorString(e)); }
-  }
+  P->host_descs.assign(descs_host, descs_host + n_desc);
 
   // ---- pass 2: work items.  Output chunks of at most 40 x 40; rows split so the batch fills the machine.
   int64_t unit_rows = 0;

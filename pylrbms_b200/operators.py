@@ -227,6 +227,11 @@ class BlockOperator(Operator):
         self.range = BlockVectorSpace(range_spaces, range_id) if self._block_range else range_spaces[0]
         self.source = BlockVectorSpace(source_spaces, source_id) if self._block_source else source_spaces[0]
         self.name = name
+        self._nonzero = [(int(i), int(j)) for i, j in zip(*np.nonzero(blocks != None))]     # noqa: E711
+
+    def nonzero_blocks(self):
+        """``[(i, j, block)]`` of the stored blocks (the block array of an S x S system is almost empty)."""
+        return [(i, j, self._blocks[i, j]) for (i, j) in self._nonzero]
 
     @property
     def num_range_blocks(self):

@@ -158,8 +158,21 @@ class _Planner:
         self.keep = []
         self.owner_rank_of = owner_rank_of or (lambda owner: 0)
         self.rank, self.world = rank, world
+        self.scratch_pool, self.scratch_used = None, []
         self._region_sizes = [0] * world
         self._pending = []            # deferred allocations: (owner_rank, size) -> resolved into offsets at finalize
+
+    def _scratch(self, rows, ld):
+        """Scratch arrays are recycled from the previous plan of the same reductor (same sizes after most enrichments)."""
+        torch = _torch()
+        pool = self.scratch_pool
+        key = (rows, ld)
+        if pool is not None and pool.get(key):
+            t = pool[key].pop()
+        else:
+            t = torch.empty((rows, ld), dtype=torch.float64, device='cuda')
+        self.scratch_used.append((key, t))
+        return t
 
     # -- output allocation: grouped per owner rank so that each rank's results are one contiguous region
     def alloc(self, owner, size):
@@ -177,9 +190,8 @@ class _Planner:
         if key in self._spmm_cache:
             return self._spmm_cache[key]
         stage = V.stage + 1
-        torch = _torch()
         ld = max(4, (V.N + 3) // 4 * 4)
-        W = torch.empty((max(1, csr.shape[0]), ld), dtype=torch.float64, device='cuda')
+        W = self._scratch(max(1, csr.shape[0]), ld)
         ref = _ArrayRef(W.data_ptr(), ld, V.N, csr.shape[0], W, stage)
         while len(self.spmm_stages) <= stage:
             self.spmm_stages.append([])
@@ -317,9 +329,7 @@ def plan_projection(op, bases, planner, owner=None, name=None):
                                     name=op.name or name)
     if isinstance(op, BlockOperator) and op._block_range and op._block_source:
         sblocks = []
-        for (i, j), b in np.ndenumerate(op._blocks):
-            if b is None:
-                continue
+        for i, j, b in op.nonzero_blocks():
             if not isinstance(b, CsrOperator):
                 raise NotImplementedError('block ({}, {}) of {} is a {}; only sparse-matrix blocks are projected'
                                           .format(i, j, op.name, type(b).__name__))
@@ -409,6 +419,13 @@ class LRBMSReductor(GenericRBSystemReductor):
         rank, world = self._shard_info()
         owner_rank_of = (lambda owner: owner_rank(owner, S, world)) if world > 1 else None
         planner = _Planner(Handle.get(), owner_rank_of, rank, world)
+        old = self.last_plan
+        if old is not None and getattr(old, 'reusable', False):
+            # the reduced model of the previous plan is no longer referenced: recycle its scratch arrays
+            pool = {}
+            for key, t in old.scratch_used:
+                pool.setdefault(key, []).append(t)
+            planner.scratch_pool = pool
         N = [len(self.bases[s.id]) for s in subs]
         V = [_ArrayRef.of(self.bases[s.id]) for s in subs]
 
@@ -469,11 +486,21 @@ class LRBMSReductor(GenericRBSystemReductor):
         self.last_plan = planner
         return planner
 
+    def _plan_key(self):
+        subs = self.d.solution_space.subspaces
+        return tuple((self.bases[s.id].device_ptr, self.bases[s.id].ld, len(self.bases[s.id])) for s in subs) + self._shard_info()
+
     def _reduce(self):
         d = self.d
-        planner = self.build_plan()
+        key = self._plan_key()
+        if self.last_plan is not None and getattr(self, '_last_key', None) == key:
+            planner = self.last_plan          # same basis buffers and sizes as last time: the plan is still valid
+        else:
+            planner = self.build_plan()
+            self._last_key = key
         planner.run()
         planner.exchange()
+        planner.reusable = True       # its SpMM scratch may be recycled by the next plan of this reductor (same stream)
         N = planner.block_dims
         fr = d.estimator.flux_reconstruction
         red_estimator = d.estimator.with_(
