@@ -398,6 +398,7 @@ class LRBMSReductor(GenericRBSystemReductor):
         self.solver_options = solver_options
         self.num_cpus = num_cpus            # accepted and ignored, like the reference (reductor.py:19,84)
         self.shard = bool(shard)
+        self.reuse_plan = False
         super().__init__(d, bases=bases, products=products)
         if order is None and bases is None:
             order = 0
@@ -493,8 +494,10 @@ class LRBMSReductor(GenericRBSystemReductor):
     def _reduce(self):
         d = self.d
         key = self._plan_key()
-        if self.last_plan is not None and getattr(self, '_last_key', None) == key:
-            planner = self.last_plan          # same basis buffers and sizes as last time: the plan is still valid
+        if self.reuse_plan and self.last_plan is not None and getattr(self, '_last_key', None) == key:
+            # same basis buffers and sizes as last time: the plan is still valid.  Opt-in, because the reduced model
+            # returned earlier shares the plan's output buffer and is overwritten by this run.
+            planner = self.last_plan
         else:
             planner = self.build_plan()
             self._last_key = key
