@@ -9,12 +9,29 @@
 
 #include "../../include/lrbms_sm100.h"
 
+constexpr int kSideStreams = 3;
+
 struct lrbms_context {
   int device = -1;
   int sm_count = 0;
   int max_smem_optin = 0;
   std::string last_error;
+  // side streams of the offline plans: the launches of one plan run (one per tile-shape bucket) are independent, so they
+  // are spread over the caller's stream and these and joined again before the plan returns (LRBMS_SINGLE_STREAM=1: off)
+  bool streams_ready = false, single_stream = false;
+  cudaStream_t side[kSideStreams] = {};
+  cudaEvent_t ev_fork = nullptr, ev_join[kSideStreams] = {};
 };
+
+// lazily creates the side streams; returns the number of streams a plan run may use (1 = caller's stream only)
+int ctx_streams(lrbms_context* ctx);
+// side streams wait for everything enqueued on `s` so far / `s` waits for everything enqueued on the side streams
+void ctx_fork(lrbms_context* ctx, cudaStream_t s);
+void ctx_join(lrbms_context* ctx, cudaStream_t s);
+inline cudaStream_t ctx_stream(lrbms_context* ctx, cudaStream_t s, int k, int n_streams) {
+  const int i = k % n_streams;
+  return i == 0 ? s : ctx->side[i - 1];
+}
 
 enum PlanKind { PLAN_SPMM = 1, PLAN_PROJECT = 2, PLAN_ONLINE = 3 };
 
@@ -94,7 +111,17 @@ __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) 
   unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s), "l"(gmem_src));
 }
+// copies with zero fill: src_bytes (<= size) bytes are read, the rest of the destination is zeroed; src must be a valid
+// address even when src_bytes == 0
+__device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gmem_src, int src_bytes) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem_src), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async8_zfill(void* smem_dst, const void* gmem_src, int src_bytes) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(s), "l"(gmem_src), "r"(src_bytes));
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 #endif

@@ -1,7 +1,37 @@
 // Context management and the GPU VectorArray backing kernels of liblrbms_sm100.
+#include <cstdlib>
+
 #include "common.cuh"
 
 thread_local std::string g_create_error;
+
+int ctx_streams(lrbms_context* ctx) {
+  if (!ctx->streams_ready) {
+    ctx->streams_ready = true;
+    const char* e = getenv("LRBMS_SINGLE_STREAM");
+    ctx->single_stream = e && e[0] == '1';
+    bool ok = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; i < kSideStreams && ok; ++i)
+      ok = cudaStreamCreateWithFlags(&ctx->side[i], cudaStreamNonBlocking) == cudaSuccess &&
+           cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) { ctx->single_stream = true; cudaGetLastError(); }
+  }
+  return ctx->single_stream ? 1 : 1 + kSideStreams;
+}
+
+void ctx_fork(lrbms_context* ctx, cudaStream_t s) {
+  if (ctx_streams(ctx) == 1) return;
+  cudaEventRecord(ctx->ev_fork, s);
+  for (int i = 0; i < kSideStreams; ++i) cudaStreamWaitEvent(ctx->side[i], ctx->ev_fork, 0);
+}
+
+void ctx_join(lrbms_context* ctx, cudaStream_t s) {
+  if (ctx_streams(ctx) == 1) return;
+  for (int i = 0; i < kSideStreams; ++i) {
+    cudaEventRecord(ctx->ev_join[i], ctx->side[i]);
+    cudaStreamWaitEvent(s, ctx->ev_join[i], 0);
+  }
+}
 
 extern "C" {
 
@@ -35,6 +65,13 @@ int lrbms_create(int device, lrbms_handle_t* out) {
 }
 
 int lrbms_destroy(lrbms_handle_t h) {
+  if (h && h->streams_ready) {
+    for (int i = 0; i < kSideStreams; ++i) {
+      if (h->side[i]) cudaStreamDestroy(h->side[i]);
+      if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
+    }
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  }
   delete h;
   return LRBMS_OK;
 }

@@ -30,6 +30,7 @@ struct ProjItem {
   int32_t slot;       // index of this item inside its group
   int32_t group_size;
   int32_t mirror;     // symmetric descriptor, off-diagonal chunk pair: also write the transposed chunk
+  int32_t diag;       // gram_kernel: diagonal chunk of a symmetric descriptor (VL and VR chunks are the same columns)
 };
 
 struct DevDesc {       // device-side mirror of lrbms_project_desc_t (VR/rowptr possibly redirected to scratch)
@@ -43,6 +44,92 @@ struct DevDesc {       // device-side mirror of lrbms_project_desc_t (VR/rowptr 
   double alpha;
 };
 
+// ------------------------------------------------------------------------------------------------------
+//  CSR walk in DMMA B-fragment layout
+// ------------------------------------------------------------------------------------------------------
+// one k-step (4 rows): b[n] = (A VR)[k0 + t][8n + g].  Lane g of row group t holds entry pb + g of its row (one
+// coalesced load per 8 entries instead of 8 broadcast loads; the first chunk arrives preloaded in myc / myv) and the
+// entries are handed round with shuffles, so the gathers of eight entries are independent and in flight together.
+// Same summation order as a serial walk of the row.
+template <int NT>
+__device__ __forceinline__ void csr_row_fragment(const int32_t* __restrict__ ci, const double* __restrict__ va, int len,
+                                                 int maxlen, int myc, double myv, const double* __restrict__ VR, int ldr,
+                                                 int nr, int g, int t, double (&b)[NT]) {
+#pragma unroll
+  for (int n = 0; n < NT; ++n) b[n] = 0.0;
+  for (int pb = 0; pb < maxlen; pb += 8) {
+    if (pb > 0) {
+      myc = 0;
+      myv = 0.0;
+      if (pb + g < len) { myc = ci[pb + g]; myv = va[pb + g]; }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (pb + j >= maxlen) break;                       // warp-uniform
+      const int src = 4 * j + t;
+      const double av = __shfl_sync(0xffffffffu, myv, src);
+      const int cj = __shfl_sync(0xffffffffu, myc, src);
+      if (pb + j < len) {
+        const double* __restrict__ vr = VR + (int64_t)cj * ldr;
+#pragma unroll
+        for (int n = 0; n < NT; ++n)
+          if (8 * n + g < nr) b[n] = fma(av, vr[8 * n], b[n]);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+//  combination of the CTAs that share one output chunk (fixed order -> bit-reproducible) and the store
+// ------------------------------------------------------------------------------------------------------
+// red: this CTA's sums in shared memory, kSlot doubles, element (a, bb) at idx(a, bb); slot_units: partial slots of
+// kPartialStride doubles one CTA occupies
+template <int kSlot, typename Idx>
+__device__ __forceinline__ void combine_and_store(const ProjItem& it, const DevDesc& D, const double* red, bool cta_any,
+                                                  int nl, int nr, double* __restrict__ partials, int32_t* __restrict__ flags,
+                                                  int32_t* __restrict__ counters, const int64_t* __restrict__ group_partial_base,
+                                                  int slot_units, int* s_last, Idx idx) {
+  const int nthreads = blockDim.x;
+  if (it.group_size == 1) {
+    for (int e = threadIdx.x; e < nl * nr; e += nthreads) {
+      const int a = e / nr, bb = e - a * nr;
+      const double v = D.alpha * red[idx(a, bb)];
+      D.out[(int64_t)(it.l0 + a) * D.ldo + it.c0 + bb] = v;
+      if (it.mirror) D.out[(int64_t)(it.c0 + bb) * D.ldo + it.l0 + a] = v;
+    }
+    return;
+  }
+  const int64_t base = group_partial_base[it.group];
+  double* my = partials + (base + (int64_t)it.slot * slot_units) * kPartialStride;
+  if (cta_any)
+    for (int e = threadIdx.x; e < kSlot; e += nthreads) my[e] = red[e];
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    flags[base + it.slot] = cta_any ? 1 : 0;
+    __threadfence();
+    const int prev = atomicAdd(&counters[it.group], 1);
+    *s_last = (prev == it.group_size - 1);
+  }
+  __syncthreads();
+  if (!*s_last) return;
+  __threadfence();
+  for (int e = threadIdx.x; e < nl * nr; e += nthreads) {
+    const int a = e / nr, bb = e - a * nr;
+    const int i = idx(a, bb);
+    double s = 0.0;
+    for (int sl = 0; sl < it.group_size; ++sl)
+      if (__ldcg(&flags[base + sl])) s += __ldcg(&partials[(base + (int64_t)sl * slot_units) * kPartialStride + i]);
+    D.out[(int64_t)(it.l0 + a) * D.ldo + it.c0 + bb] = D.alpha * s;
+    if (it.mirror) D.out[(int64_t)(it.c0 + bb) * D.ldo + it.l0 + a] = D.alpha * s;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) counters[it.group] = 0;   // self-cleaning for the next run
+}
+
+// ------------------------------------------------------------------------------------------------------
+//  project_kernel: fused G = alpha VL^T (A VR) (HAS_A) and narrow dense G = alpha VL^T VR, one 8MT x 8NT chunk per CTA
+// ------------------------------------------------------------------------------------------------------
 template <int MT, int NT, bool HAS_A>
 __global__ void __launch_bounds__(kThreads, (MT * NT <= 9) ? 3 : ((MT * NT <= 16) ? 2 : 1))
 project_kernel(const ProjItem* __restrict__ items, const DevDesc* __restrict__ descs, double* __restrict__ partials,
@@ -64,45 +151,56 @@ project_kernel(const ProjItem* __restrict__ items, const DevDesc* __restrict__ d
   const double* __restrict__ VR = D.VR + it.c0 + g;
 
   if (HAS_A) {
-    for (int k0 = it.row0 + 4 * warp; k0 < it.row1; k0 += 4 * kWarps) {
+    // Warp w owns the k-steps k0 = row0 + 4 (w + kWarps j).  32 of them are screened at once: lane j looks at the row
+    // pointers of step j, a ballot gives the steps that have non-zeros at all (coupling blocks: interface rows only).
+    // The row pointers, the first eight entries of each row and the VL fragment of the *next* live k-step are fetched
+    // before the current one is processed, so only the gathers of VR rows remain on the dependent chain of a step.
+    constexpr int kStep = 4 * kWarps;
+    int kbase = it.row0 + 4 * warp - 32 * kStep;
+    unsigned todo = 0;
+    auto next_k = [&]() -> int {
+      while (!todo) {
+        kbase += 32 * kStep;
+        if (kbase >= it.row1) return -1;
+        const int kmine = kbase + lane * kStep;
+        int has = 0;
+        if (kmine < it.row1) has = D.rowptr[min(kmine + 4, it.row1)] != D.rowptr[kmine];
+        todo = __ballot_sync(0xffffffffu, has);
+      }
+      const int j = __ffs(todo) - 1;
+      todo &= todo - 1;
+      return kbase + j * kStep;
+    };
+    struct Step { int p0, len, myc; double myv; double a[MT]; };
+    auto fetch = [&](int k0, Step& S) {
       const int row = k0 + t;
       const bool row_ok = row < it.row1;
+      S.p0 = 0; S.len = 0; S.myc = 0; S.myv = 0.0;
+      if (row_ok) {
+        S.p0 = D.rowptr[row];
+        S.len = D.rowptr[row + 1] - S.p0;
+      }
+      if (g < S.len) { S.myc = D.colind[S.p0 + g]; S.myv = D.values[S.p0 + g]; }
+      const double* __restrict__ vl = VL + (int64_t)row * D.ldl;
+#pragma unroll
+      for (int m = 0; m < MT; ++m) S.a[m] = (row_ok && 8 * m + g < nl) ? vl[8 * m] : 0.0;
+    };
+    Step cur, nxt;
+    int kcur = next_k();
+    if (kcur >= 0) fetch(kcur, cur);
+    while (kcur >= 0) {
+      const int knext = next_k();
+      if (knext >= 0) fetch(knext, nxt);
+      const int maxlen = __reduce_max_sync(0xffffffffu, cur.len);
       double b[NT];
-#pragma unroll
-      for (int n = 0; n < NT; ++n) b[n] = 0.0;
-      int p0 = 0, len = 0;
-      if (row_ok) {
-        p0 = D.rowptr[row];
-        len = D.rowptr[row + 1] - p0;
-      }
-      const int maxlen = __reduce_max_sync(0xffffffffu, len);
-      if (maxlen == 0) continue;
-      const int32_t* __restrict__ ci = D.colind + p0;
-      const double* __restrict__ va = D.values + p0;
-#pragma unroll 2
-      for (int p = 0; p < maxlen; ++p) {
-        if (p < len) {
-          const double a = va[p];
-          const double* __restrict__ vr = VR + (int64_t)ci[p] * D.ldr;
-#pragma unroll
-          for (int n = 0; n < NT; ++n)
-            if (8 * n + g < nr) b[n] = fma(a, vr[8 * n], b[n]);
-        }
-      }
+      csr_row_fragment<NT>(D.colind + cur.p0, D.values + cur.p0, cur.len, maxlen, cur.myc, cur.myv, VR, D.ldr, nr, g, t, b);
       any_work = true;
-      double a[MT];
-#pragma unroll
-      for (int m = 0; m < MT; ++m) a[m] = 0.0;
-      if (row_ok) {
-        const double* __restrict__ vl = VL + (int64_t)row * D.ldl;
-#pragma unroll
-        for (int m = 0; m < MT; ++m)
-          if (8 * m + g < nl) a[m] = vl[8 * m];
-      }
 #pragma unroll
       for (int m = 0; m < MT; ++m)
 #pragma unroll
-        for (int n = 0; n < NT; ++n) dmma884(acc[m][n][0], acc[m][n][1], a[m], b[n]);
+        for (int n = 0; n < NT; ++n) dmma884(acc[m][n][0], acc[m][n][1], cur.a[m], b[n]);
+      cur = nxt;
+      kcur = knext;
     }
   } else {
     // dense G = VL^T VR: register double buffering -- the fragments of the next k-step are in flight while the
@@ -156,48 +254,164 @@ project_kernel(const ProjItem* __restrict__ items, const DevDesc* __restrict__ d
     }
     __syncthreads();
   }
-  const bool cta_any = s_any != 0;
+  combine_and_store<MT * NT * 64>(it, D, red, s_any != 0, nl, nr, partials, flags, counters, group_partial_base, 1, &s_last,
+                                  [](int a, int bb) { return ((a >> 3) * NT + (bb >> 3)) * 64 + (a & 7) * 8 + (bb & 7); });
+}
 
-  // ---- combine the CTAs of this output group
-  if (it.group_size == 1) {
-    for (int e = threadIdx.x; e < nl * nr; e += kThreads) {
-      const int a = e / nr, bb = e - a * nr;
-      const double v = D.alpha * red[((a >> 3) * NT + (bb >> 3)) * 64 + (a & 7) * 8 + (bb & 7)];
-      D.out[(int64_t)(it.l0 + a) * D.ldo + it.c0 + bb] = v;
-      if (it.mirror) D.out[(int64_t)(it.c0 + bb) * D.ldo + it.l0 + a] = v;
+// ------------------------------------------------------------------------------------------------------
+//  gram_kernel: wide dense G = alpha VL^T VR (the estimator Grams: 100 ... 200 columns on both sides).
+//
+//  A 40 x 40 chunk per CTA needs 5 flop per byte fetched from L2 -- at the FP64 tensor rate that is ~7 TB/s of L2
+//  bandwidth, which is what the one-warp-one-chunk kernel above runs into.  Here a CTA owns a (16 WM) x (16 WN) chunk
+//  (up to 80 x 80): kGramRows rows of the VL and VR column blocks are staged once per CTA through a cp.async ring and
+//  shared by four warps, one 8 WM x 8 WN quadrant each.  Two such CTAs are resident per SM, so one CTA's barriers,
+//  pipeline fill and epilogue overlap the other's DMMAs.  Diagonal chunks of a pure Gram (VL and VR the same array) stage
+//  their columns once and use them for both operands.
+// ------------------------------------------------------------------------------------------------------
+constexpr int kGramThreads = 128;    // four warps = four quadrants; two CTAs per SM hide each other's barriers and epilogues
+constexpr int kGramRows = 16;        // rows per ring stage (4 k-steps)
+constexpr int kGramStages = 4;
+constexpr int kGramSlotUnits = 4;    // a gram partial slot = 4 project slots (100 tiles of 64 doubles)
+template <int WM, int WN>
+__host__ __device__ constexpr int gram_stride() { return 16 * WM + 16 * WN + 4; }   // = 4 mod 16: conflict-free fragment loads
+template <int WM, int WN>
+__host__ __device__ constexpr int gram_smem_doubles() {
+  return (kGramStages * kGramRows * gram_stride<WM, WN>() > 4 * WM * WN * 64) ? kGramStages * kGramRows * gram_stride<WM, WN>()
+                                                                               : 4 * WM * WN * 64;
+}
+
+template <int WM, int WN>
+__global__ void __launch_bounds__(kGramThreads, 2)
+gram_kernel(const ProjItem* __restrict__ items, const DevDesc* __restrict__ descs, double* __restrict__ partials,
+            int32_t* __restrict__ flags, int32_t* __restrict__ counters, const int64_t* __restrict__ group_partial_base) {
+  extern __shared__ __align__(16) double ring[];
+  __shared__ int s_last;
+  constexpr int S = gram_stride<WM, WN>();
+  const ProjItem it = items[blockIdx.x];
+  const DevDesc D = descs[it.desc];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int wm = warp >> 1, wn = warp & 1;
+  const int nl = min(16 * WM, D.NL - it.l0), nr = min(16 * WN, D.NR - it.c0);
+  const bool diag = it.diag != 0;                       // VL and VR chunks are the same columns: stage them once
+  const double* __restrict__ gL = D.VL + it.l0;
+  const double* __restrict__ gR = D.VR + it.c0;
+  // 16-byte copies need 16-byte aligned rows (column-slice views of a slab with an odd column offset are not)
+  const bool al16 = ((((uintptr_t)gL) | ((uintptr_t)gR)) & 15) == 0 && (D.ldl & 1) == 0 && (D.ldr & 1) == 0;
+  // columns that may be touched without leaving the row pitch (what lies between N and ld only feeds unwritten outputs)
+  const int wl = min(16 * WM, D.ldl - it.l0), wr = min(16 * WN, D.ldr - it.c0);
+  const int n_rows = it.row1 - it.row0;
+  const int n_stage = (n_rows + kGramRows - 1) / kGramRows;
+
+  // Staging: warp w copies rows 4w .. 4w + 3 of a stage; a lane takes the 16-byte (or 8-byte) chunks lane, lane + 32, ...
+  // of each row.  The per-lane column offsets and byte counts do not depend on the stage and are set up once.
+  constexpr int kChunks16 = 8 * WM + 8 * WN, kIter16 = (kChunks16 + 31) / 32;
+  constexpr int kChunks8 = 16 * WM + 16 * WN, kIter8 = (kChunks8 + 31) / 32;
+  const int n_left16 = 8 * WM, n_all16 = diag ? 8 * WM : kChunks16;
+  const int n_left8 = 16 * WM, n_all8 = diag ? 16 * WM : kChunks8;
+  auto issue = [&](int st) {
+    if (st < n_stage) {
+      double* dst = ring + (st % kGramStages) * (kGramRows * S) + 4 * warp * S;
+      const int r0 = it.row0 + st * kGramRows + 4 * warp;
+      if (al16) {
+#pragma unroll
+        for (int i = 0; i < kIter16; ++i) {
+          const int cc = lane + 32 * i;
+          if (cc < n_all16) {
+            const bool left = cc < n_left16;
+            const int col = 2 * (left ? cc : cc - n_left16);
+            const int colbytes = max(0, min(2, (left ? wl : wr) - col)) * 8;
+            const double* src0 = left ? gL + col : gR + col;
+            const int64_t ld = left ? D.ldl : D.ldr;
+            double* d0 = dst + (left ? col : 16 * WM + col);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+              const int bytes = (r0 + r < it.row1) ? colbytes : 0;
+              cp_async16_zfill(d0 + r * S, bytes ? src0 + (int64_t)(r0 + r) * ld : gL, bytes);
+            }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < kIter8; ++i) {
+          const int cc = lane + 32 * i;
+          if (cc < n_all8) {
+            const bool left = cc < n_left8;
+            const int col = left ? cc : cc - n_left8;
+            const bool col_ok = col < (left ? wl : wr);
+            const double* src0 = left ? gL + col : gR + col;
+            const int64_t ld = left ? D.ldl : D.ldr;
+            double* d0 = dst + (left ? col : 16 * WM + col);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+              const bool ok = col_ok && r0 + r < it.row1;
+              cp_async8_zfill(d0 + r * S, ok ? src0 + (int64_t)(r0 + r) * ld : gL, ok ? 8 : 0);
+            }
+          }
+        }
+      }
     }
-    return;
+    cp_async_commit();
+  };
+
+  double acc[WM][WN][2];
+#pragma unroll
+  for (int m = 0; m < WM; ++m)
+#pragma unroll
+    for (int n = 0; n < WN; ++n) acc[m][n][0] = acc[m][n][1] = 0.0;
+
+#pragma unroll
+  for (int s = 0; s < kGramStages - 1; ++s) issue(s);
+  const int aoff = wm * 8 * WM + g;
+  const int boff = (diag ? 0 : 16 * WM) + wn * 8 * WN + g;
+  for (int st = 0; st < n_stage; ++st) {
+    cp_async_wait<kGramStages - 2>();
+    __syncthreads();                       // stage st has landed for everybody; everybody is done with stage st - 1
+    issue(st + kGramStages - 1);           // ... whose buffer is refilled now
+    const double* base = ring + (st % kGramStages) * (kGramRows * S);
+    double a[2][WM], b[2][WN];
+    auto load = [&](int ks, double (&av)[WM], double (&bv)[WN]) {
+      const double* rowp = base + (4 * ks + t) * S;
+#pragma unroll
+      for (int m = 0; m < WM; ++m) av[m] = rowp[aoff + 8 * m];
+#pragma unroll
+      for (int n = 0; n < WN; ++n) bv[n] = rowp[boff + 8 * n];
+    };
+    load(0, a[0], b[0]);
+#pragma unroll
+    for (int i = 0; i < kGramRows / 4; ++i) {            // the k-steps of this stage
+      if (i + 1 < kGramRows / 4) load(i + 1, a[(i + 1) & 1], b[(i + 1) & 1]);
+#pragma unroll
+      for (int m = 0; m < WM; ++m)
+#pragma unroll
+        for (int n = 0; n < WN; ++n) dmma884(acc[m][n][0], acc[m][n][1], a[i & 1][m], b[i & 1][n]);
+    }
   }
-  const int64_t base = group_partial_base[it.group];
-  double* my = partials + (base + it.slot) * kPartialStride;
-  if (cta_any)
-    for (int e = threadIdx.x; e < MT * NT * 64; e += kThreads) my[e] = red[e];
-  __threadfence();
+  cp_async_wait<0>();
+  __syncthreads();                         // the ring is dead: its memory becomes the reduction buffer
+
+  // ---- red[quadrant][m][n][64]
+  double* red = ring;
+  const int q = wm * 2 + wn;
+#pragma unroll
+  for (int m = 0; m < WM; ++m)
+#pragma unroll
+    for (int n = 0; n < WN; ++n)
+      *reinterpret_cast<double2*>(red + ((q * WM + m) * WN + n) * 64 + g * 8 + 2 * t) = make_double2(acc[m][n][0], acc[m][n][1]);
   __syncthreads();
-  if (threadIdx.x == 0) {
-    flags[base + it.slot] = cta_any ? 1 : 0;
-    __threadfence();
-    const int prev = atomicAdd(&counters[it.group], 1);
-    s_last = (prev == it.group_size - 1);
-  }
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  for (int e = threadIdx.x; e < nl * nr; e += kThreads) {
-    const int a = e / nr, bb = e - a * nr;
-    const int idx = ((a >> 3) * NT + (bb >> 3)) * 64 + (a & 7) * 8 + (bb & 7);
-    double s = 0.0;
-    for (int sl = 0; sl < it.group_size; ++sl)
-      if (__ldcg(&flags[base + sl])) s += __ldcg(&partials[(base + sl) * kPartialStride + idx]);
-    D.out[(int64_t)(it.l0 + a) * D.ldo + it.c0 + bb] = D.alpha * s;
-    if (it.mirror) D.out[(int64_t)(it.c0 + bb) * D.ldo + it.l0 + a] = D.alpha * s;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) counters[it.group] = 0;   // self-cleaning for the next run
+  combine_and_store<4 * WM * WN * 64>(it, D, red, n_rows > 0, nl, nr, partials, flags, counters, group_partial_base,
+                                      kGramSlotUnits, &s_last, [](int a, int bb) {
+                                        const int qm = a / (8 * WM), qn = bb / (8 * WN);
+                                        const int am = a - qm * 8 * WM, bn = bb - qn * 8 * WN;
+                                        return (((qm * 2 + qn) * WM + (am >> 3)) * WN + (bn >> 3)) * 64 + (am & 7) * 8 + (bn & 7);
+                                      });
 }
 
 // ------------------------------------------------------------------------------------------------------
 //  SpMM  W = A V  in the same (row t, column 8n + g) lane layout; one warp per 4 rows and 8*NT columns.
+//  (A one-lane-per-column variant that kept the V rows of a DG element's pattern in registers was tried and dropped:
+//  three times the instructions per row at a quarter of the occupancy, 3.4 ms instead of 1.2 ms; 16-byte gathers (two
+//  columns per lane) were slower too, 1.8 ms -- profiles/README.md.)
 // ------------------------------------------------------------------------------------------------------
 struct SpmmItem { int32_t desc, row0, row1, c0; };
 
@@ -212,23 +426,23 @@ __global__ void __launch_bounds__(kThreads) spmm_kernel(const SpmmItem* __restri
   const double* __restrict__ V = D.V + it.c0 + g;
   for (int k0 = it.row0 + 4 * warp; k0 < it.row1; k0 += 4 * kWarps) {
     const int row = k0 + t;
-    if (row >= it.row1) continue;
+    const bool row_ok = row < it.row1;
+    int p0 = 0, len = 0, myc = 0;
+    double myv = 0.0;
+    if (row_ok) {
+      p0 = D.rowptr[row];
+      len = D.rowptr[row + 1] - p0;
+    }
+    if (g < len) { myc = D.colind[p0 + g]; myv = D.values[p0 + g]; }
+    const int maxlen = __reduce_max_sync(0xffffffffu, len);
     double b[NT];
-#pragma unroll
-    for (int n = 0; n < NT; ++n) b[n] = 0.0;
-    const int p0 = D.rowptr[row], p1 = D.rowptr[row + 1];
-#pragma unroll 2
-    for (int p = p0; p < p1; ++p) {
-      const double a = D.values[p];
-      const double* __restrict__ vr = V + (int64_t)D.colind[p] * D.ldv;
+    csr_row_fragment<NT>(D.colind + p0, D.values + p0, len, maxlen, myc, myv, V, D.ldv, nr, g, t, b);
+    if (row_ok) {
+      double* __restrict__ w = D.W + (int64_t)row * D.ldw + it.c0 + g;
 #pragma unroll
       for (int n = 0; n < NT; ++n)
-        if (8 * n + g < nr) b[n] = fma(a, vr[8 * n], b[n]);
+        if (8 * n + g < nr) w[8 * n] = b[n];
     }
-    double* __restrict__ w = D.W + (int64_t)row * D.ldw + it.c0 + g;
-#pragma unroll
-    for (int n = 0; n < NT; ++n)
-      if (8 * n + g < nr) w[8 * n] = b[n];
   }
 }
 
@@ -269,21 +483,32 @@ static void launch_spmm(const SpmmLaunch& L, const lrbms_spmm_desc_t* d_descs, c
   spmm_kernel<NT><<<L.n_items, kThreads, 0, s>>>(L.d_items, d_descs);
 }
 
+static void dispatch_spmm(const SpmmLaunch& L, const lrbms_spmm_desc_t* d_descs, cudaStream_t s) {
+  switch (L.nt) {
+    case 1: launch_spmm<1>(L, d_descs, s); break;
+    case 2: launch_spmm<2>(L, d_descs, s); break;
+    case 3: launch_spmm<3>(L, d_descs, s); break;
+    case 4: launch_spmm<4>(L, d_descs, s); break;
+    case 5: launch_spmm<5>(L, d_descs, s); break;
+    case 6: launch_spmm<6>(L, d_descs, s); break;
+    case 7: launch_spmm<7>(L, d_descs, s); break;
+    default: launch_spmm<8>(L, d_descs, s); break;
+  }
+}
+
+// launches are kept sorted by size (largest first) and dealt round-robin to the caller's stream and the side streams
 int SpmmPlan::run(void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
+  int n_live = 0;
+  for (const SpmmLaunch& L : launches) n_live += L.n_items > 0;
+  const int ns = n_live > 1 ? ctx_streams(ctx) : 1;
+  if (ns > 1) ctx_fork(ctx, s);
+  int k = 0;
   for (const SpmmLaunch& L : launches) {
     if (!L.n_items) continue;
-    switch (L.nt) {
-      case 1: launch_spmm<1>(L, d_descs, s); break;
-      case 2: launch_spmm<2>(L, d_descs, s); break;
-      case 3: launch_spmm<3>(L, d_descs, s); break;
-      case 4: launch_spmm<4>(L, d_descs, s); break;
-      case 5: launch_spmm<5>(L, d_descs, s); break;
-      case 6: launch_spmm<6>(L, d_descs, s); break;
-      case 7: launch_spmm<7>(L, d_descs, s); break;
-      default: launch_spmm<8>(L, d_descs, s); break;
-    }
+    dispatch_spmm(L, d_descs, ctx_stream(ctx, s, k++, ns));
   }
+  if (ns > 1) ctx_join(ctx, s);
   LRBMS_CUDA_CHECK(ctx, cudaGetLastError());
   return LRBMS_OK;
 }
@@ -292,7 +517,7 @@ int SpmmPlan::run(void* stream) {
 static void build_spmm_items(const std::vector<lrbms_spmm_desc_t>& descs, int sm_count,
                              std::vector<std::vector<SpmmItem>>& by_nt /* index nt-1 */) {
   by_nt.assign(8, {});
-  // rows per CTA: aim at >= 4 CTAs per SM over the whole batch, in multiples of 32 rows (one k-step per warp)
+  // rows per CTA: aim at >= 8 CTAs per SM over the whole batch, in multiples of 32 rows (one k-step per warp)
   int64_t total_rows = 0;
   for (const auto& d : descs) total_rows += (int64_t)d.n_rows * ((d.N + 63) / 64);
   int64_t target_ctas = (int64_t)sm_count * 8;
@@ -311,8 +536,9 @@ static void build_spmm_items(const std::vector<lrbms_spmm_desc_t>& descs, int sm
 }
 
 struct ProjLaunch {
-  int mt, nt;
+  int mt, nt;         // tiles per CTA chunk (project_kernel) or per warp quadrant (gram_kernel)
   bool has_a;
+  bool gram = false;
   ProjItem* d_items = nullptr;
   int n_items = 0;
 };
@@ -361,6 +587,35 @@ static void dispatch_mt(const ProjLaunch& L, const ProjectPlan* P, cudaStream_t 
   }
 }
 
+template <int WM, int WN>
+static void launch_gram(const ProjLaunch& L, const ProjectPlan* P, cudaStream_t s) {
+  const size_t smem = sizeof(double) * gram_smem_doubles<WM, WN>();
+  cudaFuncSetAttribute(gram_kernel<WM, WN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  gram_kernel<WM, WN><<<L.n_items, kGramThreads, smem, s>>>(L.d_items, P->d_descs, P->d_partials, P->d_flags, P->d_counters,
+                                                        P->d_group_base);
+}
+
+template <int WM>
+static void dispatch_gram_n(const ProjLaunch& L, const ProjectPlan* P, cudaStream_t s) {
+  switch (L.nt) {
+    case 1: launch_gram<WM, 1>(L, P, s); break;
+    case 2: launch_gram<WM, 2>(L, P, s); break;
+    case 3: launch_gram<WM, 3>(L, P, s); break;
+    case 4: launch_gram<WM, 4>(L, P, s); break;
+    default: launch_gram<WM, 5>(L, P, s); break;
+  }
+}
+
+static void dispatch_gram(const ProjLaunch& L, const ProjectPlan* P, cudaStream_t s) {
+  switch (L.mt) {
+    case 1: dispatch_gram_n<1>(L, P, s); break;
+    case 2: dispatch_gram_n<2>(L, P, s); break;
+    case 3: dispatch_gram_n<3>(L, P, s); break;
+    case 4: dispatch_gram_n<4>(L, P, s); break;
+    default: dispatch_gram_n<5>(L, P, s); break;
+  }
+}
+
 // accounting (tight and SURVEY-formula byte counts) from the device CSR data; lazy because it costs two small kernels
 // and two synchronous copies per descriptor
 void ProjectPlan::ensure_info() {
@@ -397,25 +652,35 @@ void ProjectPlan::ensure_info() {
   cudaFree(d_flag);
 }
 
+// Phase 1: the scratch SpMMs of the two-step descriptors and the fused projections (independent of each other);
+// phase 2: the dense projections, which read the SpMM scratch.  Inside a phase the launches are spread over streams.
 int ProjectPlan::run(void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
+  int n_live = 0;
+  for (const SpmmLaunch& L : spmm_launches) n_live += L.n_items > 0;
+  for (const ProjLaunch& L : launches) n_live += L.n_items > 0;
+  const int ns = n_live > 1 ? ctx_streams(ctx) : 1;
+  if (ns > 1) ctx_fork(ctx, s);
+  int k = 0;
+  bool any_spmm = false;
   for (const SpmmLaunch& L : spmm_launches) {
     if (!L.n_items) continue;
-    switch (L.nt) {
-      case 1: launch_spmm<1>(L, d_spmm_descs, s); break;
-      case 2: launch_spmm<2>(L, d_spmm_descs, s); break;
-      case 3: launch_spmm<3>(L, d_spmm_descs, s); break;
-      case 4: launch_spmm<4>(L, d_spmm_descs, s); break;
-      case 5: launch_spmm<5>(L, d_spmm_descs, s); break;
-      case 6: launch_spmm<6>(L, d_spmm_descs, s); break;
-      case 7: launch_spmm<7>(L, d_spmm_descs, s); break;
-      default: launch_spmm<8>(L, d_spmm_descs, s); break;
-    }
+    any_spmm = true;
+    dispatch_spmm(L, d_spmm_descs, ctx_stream(ctx, s, k++, ns));
+  }
+  for (const ProjLaunch& L : launches)
+    if (L.n_items && L.has_a) dispatch_mt<true>(L, this, ctx_stream(ctx, s, k++, ns));
+  if (ns > 1 && any_spmm) {
+    ctx_join(ctx, s);
+    ctx_fork(ctx, s);
+    k = 0;
   }
   for (const ProjLaunch& L : launches) {
-    if (!L.n_items) continue;
-    if (L.has_a) dispatch_mt<true>(L, this, s); else dispatch_mt<false>(L, this, s);
+    if (!L.n_items || L.has_a) continue;
+    if (L.gram) dispatch_gram(L, this, ctx_stream(ctx, s, k++, ns));
+    else dispatch_mt<false>(L, this, ctx_stream(ctx, s, k++, ns));
   }
+  if (ns > 1) ctx_join(ctx, s);
   LRBMS_CUDA_CHECK(ctx, cudaGetLastError());
   return LRBMS_OK;
 }
@@ -449,6 +714,8 @@ int lrbms_spmm_plan_create(lrbms_handle_t h, int32_t n_desc, const lrbms_spmm_de
     P->info_launches += 1;
     P->info_ctas += L.n_items;
   }
+  std::stable_sort(P->launches.begin(), P->launches.end(),
+                   [](const SpmmLaunch& a, const SpmmLaunch& b) { return (int64_t)a.n_items * a.nt > (int64_t)b.n_items * b.nt; });
   if (rc) { lrbms_plan_destroy(P); return rc; }
   // accounting: nnz from the device row pointers
   for (const auto& d : descs) {
@@ -506,51 +773,60 @@ int lrbms_project_plan_create(lrbms_handle_t h, int32_t n_desc, const lrbms_proj
 
   P->host_descs.assign(descs_host, descs_host + n_desc);
 
-  // ---- pass 2: work items.  Output chunks of at most 40 x 40; rows split so the batch fills the machine.
+  // ---- pass 2: work items.  Output chunks of at most 40 x 40 (project_kernel) or 80 x 80 (gram_kernel: dense with more
+  //      than 40 columns on both sides); rows split so the batch fills the machine.
+  auto is_gram = [&](const DevDesc& x) { return !x.rowptr && x.NL > 8 * kMaxTile && x.NR > 8 * kMaxTile; };
   int64_t unit_rows = 0;
   for (int i = 0; i < n_desc; ++i) {
     const auto& x = dd[i];
-    int64_t chunks = (int64_t)((x.NL + 8 * kMaxTile - 1) / (8 * kMaxTile)) * ((x.NR + 8 * kMaxTile - 1) / (8 * kMaxTile));
-    unit_rows += chunks * x.n_rows;
+    const int cw = is_gram(x) ? 16 * kMaxTile : 8 * kMaxTile;
+    int64_t chunks = (int64_t)((x.NL + cw - 1) / cw) * ((x.NR + cw - 1) / cw);
+    unit_rows += chunks * x.n_rows * (is_gram(x) ? 3 : 1);     // a gram CTA does four times the work with one CTA per SM
   }
   const int64_t target_ctas = (int64_t)h->sm_count * 12;
   int64_t rows_per_cta = std::max<int64_t>(128, ((unit_rows / std::max<int64_t>(1, target_ctas) + 31) / 32) * 32);
   rows_per_cta = std::min<int64_t>(rows_per_cta, 2048);
 
-  struct Key { int mt, nt; bool has_a; };
-  std::vector<std::vector<ProjItem>> buckets(kMaxTile * kMaxTile * 2);
+  std::vector<std::vector<ProjItem>> buckets(kMaxTile * kMaxTile * 3);   // [(mt, nt)][dense, fused, gram]
   std::vector<int64_t> group_base;
   int64_t n_partials = 0;   // partial slots, kPartialStride doubles each
   int32_t n_groups = 0;
   for (int i = 0; i < n_desc; ++i) {
     const auto& x = dd[i];
-    const int n_lch = (x.NL + 8 * kMaxTile - 1) / (8 * kMaxTile), n_rch = (x.NR + 8 * kMaxTile - 1) / (8 * kMaxTile);
+    const bool gram = is_gram(x);
+    const int max_ct = gram ? 2 * kMaxTile : kMaxTile;           // tiles per chunk
     // balanced chunk widths (e.g. 100 -> 3 chunks of 40, 32, 32 is worse than 3 x 5 tiles, 4, 4): use tiles
     const int lt = (x.NL + 7) / 8, rt = (x.NR + 7) / 8;
+    const int n_lch = (lt + max_ct - 1) / max_ct, n_rch = (rt + max_ct - 1) / max_ct;
     const bool symmetric = descs_host[i].symmetric != 0 && x.NL == x.NR;
+    const int row_quant = gram ? kGramRows : 4;
     for (int lc = 0; lc < n_lch; ++lc) {
       const int lt0 = (int)((int64_t)lt * lc / n_lch), lt1 = (int)((int64_t)lt * (lc + 1) / n_lch);
       for (int rc_ = 0; rc_ < n_rch; ++rc_) {
         if (symmetric && rc_ > lc) continue;          // upper chunks are mirrored from the lower ones
         const int rt0 = (int)((int64_t)rt * rc_ / n_rch), rt1 = (int)((int64_t)rt * (rc_ + 1) / n_rch);
-        const int mt = lt1 - lt0, nt = rt1 - rt0;
-        const int n_split = (int)std::max<int64_t>(1, (x.n_rows + rows_per_cta - 1) / rows_per_cta);
-        const int64_t rows_each = ((((int64_t)x.n_rows + n_split - 1) / n_split) + 3) / 4 * 4;
+        // project_kernel: tiles per CTA; gram_kernel: tiles per warp quadrant (two quadrants per direction)
+        const int mt = gram ? (lt1 - lt0 + 1) / 2 : lt1 - lt0, nt = gram ? (rt1 - rt0 + 1) / 2 : rt1 - rt0;
+        const int64_t rpc = rows_per_cta;
+        const int n_split = (int)std::max<int64_t>(1, (x.n_rows + rpc - 1) / rpc);
+        const int64_t rows_each = std::max<int64_t>(
+            row_quant, ((((int64_t)x.n_rows + n_split - 1) / n_split) + row_quant - 1) / row_quant * row_quant);
         const int32_t group = n_groups++;
         group_base.push_back(n_partials);
         int slot = 0;
-        std::vector<ProjItem>& bucket = buckets[((mt - 1) * kMaxTile + (nt - 1)) * 2 + (x.rowptr ? 1 : 0)];
+        std::vector<ProjItem>& bucket = buckets[((mt - 1) * kMaxTile + (nt - 1)) * 3 + (gram ? 2 : (x.rowptr ? 1 : 0))];
         const size_t first = bucket.size();
-        for (int64_t r0 = 0; r0 < std::max(1, x.n_rows); r0 += std::max<int64_t>(4, rows_each)) {
+        for (int64_t r0 = 0; r0 < std::max(1, x.n_rows); r0 += rows_each) {
           ProjItem it;
           it.desc = i; it.l0 = 8 * lt0; it.c0 = 8 * rt0;
-          it.row0 = (int32_t)r0; it.row1 = (int32_t)std::min<int64_t>(x.n_rows, r0 + std::max<int64_t>(4, rows_each));
+          it.row0 = (int32_t)r0; it.row1 = (int32_t)std::min<int64_t>(x.n_rows, r0 + rows_each);
           it.group = group; it.slot = slot++; it.group_size = 0;
           it.mirror = (symmetric && rc_ != lc) ? 1 : 0;
+          it.diag = (gram && symmetric && rc_ == lc && x.VL == x.VR && x.ldl == x.ldr) ? 1 : 0;
           bucket.push_back(it);
         }
         for (size_t k = first; k < bucket.size(); ++k) bucket[k].group_size = slot;
-        if (slot > 1) n_partials += slot;
+        if (slot > 1) n_partials += (int64_t)slot * (gram ? kGramSlotUnits : 1);
       }
     }
   }
@@ -565,11 +841,11 @@ int lrbms_project_plan_create(lrbms_handle_t h, int32_t n_desc, const lrbms_proj
   }
   for (int mt = 1; mt <= kMaxTile && !rc; ++mt)
     for (int nt = 1; nt <= kMaxTile && !rc; ++nt)
-      for (int ha = 0; ha < 2 && !rc; ++ha) {
-        auto& bucket = buckets[((mt - 1) * kMaxTile + (nt - 1)) * 2 + ha];
+      for (int kind = 0; kind < 3 && !rc; ++kind) {
+        auto& bucket = buckets[((mt - 1) * kMaxTile + (nt - 1)) * 3 + kind];
         if (bucket.empty()) continue;
         ProjLaunch L;
-        L.mt = mt; L.nt = nt; L.has_a = ha != 0; L.n_items = (int)bucket.size();
+        L.mt = mt; L.nt = nt; L.has_a = kind == 1; L.gram = kind == 2; L.n_items = (int)bucket.size();
         rc = plan_upload(P, &L.d_items, bucket);
         P->launches.push_back(L);
         P->info_launches += 1;
@@ -588,6 +864,11 @@ int lrbms_project_plan_create(lrbms_handle_t h, int32_t n_desc, const lrbms_proj
       P->info_launches += 1;
     }
   }
+  std::stable_sort(P->spmm_launches.begin(), P->spmm_launches.end(),
+                   [](const SpmmLaunch& a, const SpmmLaunch& b) { return (int64_t)a.n_items * a.nt > (int64_t)b.n_items * b.nt; });
+  std::stable_sort(P->launches.begin(), P->launches.end(), [](const ProjLaunch& a, const ProjLaunch& b) {
+    return (int64_t)a.n_items * a.mt * a.nt * (a.gram ? 4 : 1) > (int64_t)b.n_items * b.mt * b.nt * (b.gram ? 4 : 1);
+  });
   if (rc) { lrbms_plan_destroy(P); return rc; }
   *out = P;
   return LRBMS_OK;
