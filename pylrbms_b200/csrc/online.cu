@@ -736,8 +736,10 @@ solve_kernel_v2(SolveParamsV2 P2, int64_t n_mu, const double* __restrict__ theta
 // ------------------------------------------------------------------------------------------------------
 constexpr int kEstThreads = 512;
 constexpr int kEstWarps = kEstThreads / 32;
-constexpr int kTMU = 64;         // parameters per CTA: every estimator matrix is read once per 64 parameters
-constexpr int kLDX = 68;         // shared row stride (doubles): 68 mod 16 == 4 -> conflict-free DMMA fragment loads
+// parameters per CTA (template argument kTMU: 64, 32, 16 or 8): every estimator matrix is read once per kTMU parameters.
+// 64 unless the neighbourhood vectors of that many parameters do not fit the shared memory (3D neighbourhoods, N = 40).
+// shared row stride kTMU + 4 (doubles): 4 or 12 mod 16 -> conflict-free DMMA fragment loads
+constexpr int kTMUMax = 64;
 constexpr int kMaxEstTerms = 64; // terms per subdomain
 
 struct DevTerm {
@@ -757,9 +759,11 @@ struct EstParams {
   const double* r_scale;
 };
 
+template <int kTMU>
 __global__ void __launch_bounds__(kEstThreads, 1)
 estimate_kernel(EstParams P, int64_t n_mu, const double* __restrict__ theta, const double* __restrict__ u,
                 double* __restrict__ parts) {
+  constexpr int kLDX = kTMU + 4;
   extern __shared__ double smem[];
   double* XN = smem;                                   // dmax_pad x kLDX
   double* XR = XN + (int64_t)P.dmax_pad * kLDX;        // qdmax_pad x kLDX
@@ -948,6 +952,7 @@ struct OnlinePlan : lrbms_plan {
   CombineParams cp;
   int solve_grid = 0;
   size_t solve_smem = 0, est_smem = 0;
+  int est_tmu = kTMUMax;        // parameters per estimator CTA
   bool has_estimator = false;
   int run(void*) override { return lrbms_fail(ctx, LRBMS_ERR_INVALID, "online plans are run with lrbms_online_*"); }
 };
@@ -1154,13 +1159,22 @@ int lrbms_online_plan_create(lrbms_handle_t h, const lrbms_reduced_system_t* sys
     std::vector<double> rf2(sys->rf_squared, sys->rf_squared + S.n_sub), rs(sys->r_scale, sys->r_scale + S.n_sub);
     UP_F64(ep.rf2, rf2);
     UP_F64(ep.r_scale, rs);
-    P->est_smem = sizeof(double) * ((size_t)(ep.dmax_pad + ep.qdmax_pad) * kLDX + (size_t)Q * kTMU + kEstWarps * 3 * kTMU);
+    auto est_bytes = [&](int tmu) {
+      return sizeof(double) * ((size_t)(ep.dmax_pad + ep.qdmax_pad) * (tmu + 4) + (size_t)Q * tmu + kEstWarps * 3 * tmu);
+    };
+    P->est_tmu = kTMUMax;
+    while (P->est_tmu > 8 && est_bytes(P->est_tmu) > (size_t)h->max_smem_optin) P->est_tmu /= 2;
+    P->est_smem = est_bytes(P->est_tmu);
     if (P->est_smem > (size_t)h->max_smem_optin) {
       lrbms_plan_destroy(P);
       return lrbms_fail(h, LRBMS_ERR_UNSUPPORTED, "online_plan_create: neighbourhood too large for the estimator kernel's shared memory");
     }
-    if (P->est_smem > 48 * 1024)
-      LRBMS_CUDA_CHECK(h, cudaFuncSetAttribute(estimate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->est_smem));
+    if (P->est_smem > 48 * 1024) {
+      const void* fn = P->est_tmu == 64 ? (const void*)estimate_kernel<64>
+                       : P->est_tmu == 32 ? (const void*)estimate_kernel<32>
+                       : P->est_tmu == 16 ? (const void*)estimate_kernel<16> : (const void*)estimate_kernel<8>;
+      LRBMS_CUDA_CHECK(h, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->est_smem));
+    }
     CombineParams& cp = P->cp;
     cp.n_sub = S.n_sub; cp.Q = Q; cp.n_theta = Q + Qf; cp.alpha_first = sys->alpha_returns_first;
     for (int q = 0; q < Q; ++q) { cp.theta_bar[q] = sys->theta_bar[q]; cp.theta_hat[q] = sys->theta_hat[q]; }
@@ -1217,8 +1231,13 @@ int lrbms_online_estimate(lrbms_plan_t plan, int64_t n_mu, const double* theta, 
     LRBMS_REQUIRE(P->ctx, workspace && workspace_bytes >= off + parts_ws_bytes(P, n_mu), "online_estimate: workspace too small");
     pbuf = reinterpret_cast<double*>(reinterpret_cast<char*>(workspace) + off);
   }
-  dim3 grid((unsigned)((n_mu + kTMU - 1) / kTMU), (unsigned)P->sym.n_sub);
-  estimate_kernel<<<grid, kEstThreads, P->est_smem, (cudaStream_t)stream>>>(P->ep, n_mu, theta, u, pbuf);
+  const int tmu = P->est_tmu;
+  dim3 grid((unsigned)((n_mu + tmu - 1) / tmu), (unsigned)P->sym.n_sub);
+  cudaStream_t es = (cudaStream_t)stream;
+  if (tmu == 64) estimate_kernel<64><<<grid, kEstThreads, P->est_smem, es>>>(P->ep, n_mu, theta, u, pbuf);
+  else if (tmu == 32) estimate_kernel<32><<<grid, kEstThreads, P->est_smem, es>>>(P->ep, n_mu, theta, u, pbuf);
+  else if (tmu == 16) estimate_kernel<16><<<grid, kEstThreads, P->est_smem, es>>>(P->ep, n_mu, theta, u, pbuf);
+  else estimate_kernel<8><<<grid, kEstThreads, P->est_smem, es>>>(P->ep, n_mu, theta, u, pbuf);
   combine_kernel<<<(unsigned)((n_mu + 127) / 128), 128, 0, (cudaStream_t)stream>>>(P->cp, n_mu, theta, pbuf, eta, indicators);
   LRBMS_CUDA_CHECK(P->ctx, cudaGetLastError());
   return LRBMS_OK;

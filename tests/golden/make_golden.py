@@ -20,6 +20,9 @@ CASES = {
     # name: (num_subdomains, cells_per_subdomain, basis sizes, basis seed, mu_bar, mu_hat)
     'os2015_2x2_N5': ((2, 2), 4, 5, 1001, 1.0, 1.0),
     'os2015_3x2_ragged': ((3, 2), 4, [3, 7, 4, 6, 5, 8], 1002, 0.6, 0.3),
+    # 3D structure of BASELINE.json config C4 (six face neighbours) on seeded synthetic operators
+    # (pylrbms_b200/synthetic_fixture.py): (grid, cells per subdomain and direction), ragged basis sizes
+    'synthetic3d_3x2x2_ragged': ((3, 2, 2), (2, 2, 2), [5, 6, 7, 4, 8, 6, 5, 7, 6, 5, 4, 6], 1004, 0.7, 0.4),
 }
 MUS = np.array([0.1, 0.25, 0.5, 0.8, 1.0])
 
@@ -40,6 +43,10 @@ def input_digest(data, bases):
 def build_case(name):
     from pylrbms_b200.swipdg_fixture import assemble_block_swipdg, make_local_bases, os2015_problem
     num_subdomains, cells, sizes, seed, mu_bar, mu_hat = CASES[name]
+    if isinstance(cells, tuple):
+        from pylrbms_b200.synthetic_fixture import make_random_local_bases, synthetic_block_operators
+        data = synthetic_block_operators(num_subdomains, cells, seed=seed, problem=os2015_problem(mu_bar=mu_bar, mu_hat=mu_hat))
+        return data, make_random_local_bases(data, sizes, seed=seed)
     data = assemble_block_swipdg(num_subdomains, cells, problem=os2015_problem(mu_bar=mu_bar, mu_hat=mu_hat))
     bases = make_local_bases(data, sizes, seed=seed)
     return data, bases

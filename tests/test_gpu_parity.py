@@ -18,8 +18,13 @@ def _setup(num_subdomains, cells, basis_size, seed, problem=None):
     from pylrbms_b200.swipdg_fixture import assemble_block_swipdg, make_local_bases
     from pylrbms_b200 import discretize, LRBMSReductor
     from oracle import lrbms_oracle as O
-    data = assemble_block_swipdg(num_subdomains, cells, problem=problem)
-    bases = make_local_bases(data, basis_size, seed=seed)
+    if isinstance(cells, tuple):        # seeded synthetic operators with 3D structure (synthetic_fixture.py)
+        from pylrbms_b200.synthetic_fixture import make_random_local_bases, synthetic_block_operators
+        data = synthetic_block_operators(num_subdomains, cells, seed=1000 + seed)
+        bases = make_random_local_bases(data, basis_size, seed=seed)
+    else:
+        data = assemble_block_swipdg(num_subdomains, cells, problem=problem)
+        bases = make_local_bases(data, basis_size, seed=seed)
     S = data.num_subdomains
     d_ref = O.build_discretization(data)
     red_ref = O.LRBMSReductor(d_ref, bases={'domain_%d' % i: bases[i] for i in range(S)})
@@ -52,6 +57,10 @@ CASES = [
     ((2, 2), 4, 5, 1),                       # tiny
     ((3, 2), 4, [3, 7, 4, 6, 5, 8], 2),      # ragged local basis sizes (after enrichment, online_enrichment.py:49-51)
     ((4, 4), 8, 8, 3),                       # C1-like
+    # 3D structure of config C4 (six face neighbours), synthetic operators
+    ((2, 2, 2), (2, 2, 2), [5, 6, 7, 4, 8, 6, 5, 7], 11),
+    ((3, 3, 3), (2, 2, 2), 8, 12),           # the centre subdomain has a seven-member neighbourhood
+    ((3, 3, 3), (3, 3, 3), 40, 13),          # N = 40: global-scratch solve kernel, 16-parameter estimator CTAs
 ]
 
 
