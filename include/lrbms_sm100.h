@@ -213,6 +213,20 @@ int lrbms_online_debug_timing(lrbms_plan_t plan, int64_t* out_host, int32_t n);
 /* max and argmax of eta (device outputs: max_out[1], argmax_out[1]); the per-GPU leg of the estimator-max gather */
 int lrbms_eta_max(lrbms_handle_t h, int64_t n_mu, const double* eta, double* max_out, int64_t* argmax_out, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------- */
+/*  Fine-scale neighbourhood solve of the local corrector problems          */
+/*  replaces: lhs.apply_inverse(rhs.as_source_array(mu), mu, inverse_options) on the neighbourhood system   */
+/*  assembled by solve_for_local_correction (discretize_elliptic_block_swipdg.py:227-316; dune-istl in the   */
+/*  reference), called from LRBMSReductor.enrich_local (reductor.py:75-78).                                 */
+/*  Jacobi-preconditioned CG on a device CSR matrix; x holds the initial guess on entry and the solution on  */
+/*  exit; stops when ||b - A x||_2 <= rtol ||b||_2 or after max_iter iterations (not an error: inspect       */
+/*  relres_out).  Returns LRBMS_ERR_NOT_SPD when p^T A p <= 0 is met.  iters_out / relres_out are host.      */
+/* ---------------------------------------------------------------------------------------------------- */
+int lrbms_pcg_workspace_bytes(lrbms_handle_t h, int64_t n, size_t* bytes);
+int lrbms_pcg_solve(lrbms_handle_t h, int32_t n, const int32_t* rowptr, const int32_t* colind, const double* values,
+                    const double* b, double* x, double rtol, int32_t max_iter, int32_t* iters_out, double* relres_out,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

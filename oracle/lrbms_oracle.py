@@ -18,6 +18,7 @@ Restated here:
 from __future__ import annotations
 
 import numpy as np
+import scipy.sparse as sp
 
 from .pymor_like import (VA, BlockVA, Space, BlockSpace, MatrixOperator, VectorFunctional, VectorArrayOperator,
                          LincombOperator, Concatenation, BlockOperator, BlockDiagonalOperator,
@@ -117,6 +118,27 @@ class Discretization:
     def estimate(self, U, mu=None, decompose=False):
         mu = self.parse_parameter(mu)
         return self.estimator.estimate(U, mu, self, decompose=decompose)
+
+    def solve_for_local_correction(self, subdomain, Us, mu=None, inverse_options=None):
+        """reference discretize...:227-316: solve the corrector problem on the neighbourhood of ``subdomain`` and restrict
+        the solution to the subdomain.  The reference assembles the neighbourhood operator with dune-gdt (not available);
+        the restatement uses the principal submatrix of the global block operator over the neighbourhood and a sparse
+        direct solve -- the same definition the CUDA path uses with its PCG solver.  ``Us`` does not enter (the boundary
+        functional of the current solution is commented out in the reference, ``:247-260``)."""
+        import scipy.sparse.linalg as spla
+        mu = self.parse_parameter(mu)
+        nb = list(self.neighborhoods[subdomain])
+        A = None
+        for op, c in zip(self.operator.operators, self.operator.coefficients):
+            blocks = [[(op._blocks[k, l].matrix if op._blocks[k, l] is not None else None) for l in nb] for k in nb]
+            M = sp.bmat(blocks, format='csc')
+            theta = c.evaluate(mu) if hasattr(c, 'evaluate') else float(c)
+            A = theta * M if A is None else A + theta * M
+        f = np.concatenate([self.rhs.operators[0]._array._blocks[k].data[0] for k in nb])
+        x = spla.spsolve(A.tocsc(), f)
+        sizes = [self.solution_space.subspaces[k].dim for k in nb]
+        start = int(np.sum(sizes[:nb.index(subdomain)]))
+        return self.solution_space.subspaces[subdomain].make_array(x[start:start + sizes[nb.index(subdomain)]][None, :])
 
     def shape_functions(self, subdomain, order=0):
         """reference discretize...:187-200: constant 1, then x, y, x*y (nodal interpolants here)."""
@@ -413,21 +435,32 @@ class GenericRBSystemReductor:
         rd.block_dims = [len(self.bases[s.id]) for s in d.solution_space.subspaces]
         return rd
 
+    def _offsets_of(self, u):
+        """pyMOR semantics ``RB[:u.dim].lincomb(u)``: the block sizes are those of the reduced model ``u`` came from."""
+        subs = self.d.solution_space.subspaces
+        dims = getattr(u, 'block_dims', None)
+        if dims is None:
+            dims = [len(self.bases[s.id]) for s in subs]
+        return np.cumsum([0] + list(dims))
+
     def reconstruct(self, u):
         subs = self.d.solution_space.subspaces
-        offs = np.cumsum([0] + [len(self.bases[s.id]) for s in subs])
-        return self.d.solution_space.make_array(
-            [self.bases[s.id].lincomb(u.data[:, offs[k]:offs[k + 1]]) for k, s in enumerate(subs)])
+        return self.d.solution_space.make_array([self.reconstruct_local(u, s.id) for s in subs])
 
     def reconstruct_local(self, u, space_id):
         subs = self.d.solution_space.subspaces
-        offs = np.cumsum([0] + [len(self.bases[s.id]) for s in subs])
+        offs = self._offsets_of(u)
         k = [s.id for s in subs].index(space_id)
-        return self.bases[space_id].lincomb(u.data[:, offs[k]:offs[k + 1]])
+        n = int(offs[k + 1] - offs[k])
+        basis = self.bases[space_id]
+        return VA(np.atleast_2d(u.data[:, offs[k]:offs[k + 1]]) @ basis.data[:n], basis.space)
 
 
 class ReducedDiscretization(Discretization):
-    pass
+    def solve(self, mu=None):
+        U = super().solve(mu)
+        U.block_dims = list(getattr(self, 'block_dims', [])) or None
+        return U
 
 
 class LRBMSReductor(GenericRBSystemReductor):
@@ -476,6 +509,73 @@ class LRBMSReductor(GenericRBSystemReductor):
         rd = super()._reduce()
         rd = rd.with_(estimator=red_estimator)
         return rd
+
+
+    def enrich_local(self, subdomain, U, mu=None):
+        """reference reductor.py:75-78."""
+        Us = [self.reconstruct_local(U, 'domain_{}'.format(sdi)) for sdi in self.d.neighborhoods[subdomain]]
+        local_correction = self.d.solve_for_local_correction(subdomain, Us, mu, inverse_options=self.solver_options)
+        self.extend_basis_local(local_correction)
+
+
+# ----------------------------------------------------------------------------------------------------------
+#  online adaptive enrichment (reference online_enrichment.py)
+# ----------------------------------------------------------------------------------------------------------
+
+def doerfler_marking(indicators, theta):
+    """reference online_enrichment.py:9-22, line by line."""
+    assert 0.0 < theta <= 1.0
+    indices = list(range(len(indicators)))
+    indicators = [ii ** 2 for ii in indicators]
+    indicators, indices = [list(x) for x in zip(*sorted(zip(indicators, indices), key=lambda pair: pair[0], reverse=True))]
+    total = np.sum(indicators)
+    sums = np.array([np.sum(indicators[:ii + 1]) for ii in np.arange(len(indicators))])
+    where = sums > theta * total
+    if np.any(where):
+        return indices[:np.argmax(where) + 1]
+    return indices
+
+
+class AdaptiveEnrichment:
+    """reference online_enrichment.py:25-93 (logging dropped; marked subdomains enriched in ascending order)."""
+
+    def __init__(self, grid_and_problem_data, discretization, block_space, reductor, rd,
+                 target_error, marking_doerfler_theta, marking_max_age):
+        self.discretization, self.block_space, self.reductor, self.rd = discretization, block_space, reductor, rd
+        self.target_error = target_error
+        self.marking_doerfler_theta = marking_doerfler_theta
+        self.marking_max_age = marking_max_age
+        self.num_blocks = len(block_space.subspaces)
+
+    def _enrich_once(self, U, mu, indicators, age_count):
+        marked = set(doerfler_marking(indicators, self.marking_doerfler_theta))
+        for ii in np.where(age_count > self.marking_max_age)[0]:
+            marked.add(int(ii))
+        for ii in sorted(marked):
+            self.reductor.enrich_local(ii, U, mu)
+        self.rd = self.reductor.reduce()
+        for ii in range(self.num_blocks):
+            if ii in marked:
+                age_count[ii] = 1
+            else:
+                age_count[ii] += 1
+        return len(marked)
+
+    def solve(self, mu, enrichment_steps=np.inf, callback=None):
+        mu = self.discretization.parse_parameter(mu)
+        enrichment_step = 1
+        age_count = np.ones(self.num_blocks)
+        local_problem_solves = 0
+        while True:
+            U = self.rd.solve(mu)
+            eta, _, indicators = self.rd.estimate(U, mu=mu, decompose=True)
+            if callback:
+                callback(self.rd, U, mu, {'eta': eta, 'local_problem_solves': local_problem_solves,
+                                          'global RB size': self.rd.solution_space.dim})
+            if eta <= self.target_error or enrichment_step > enrichment_steps:
+                return U, self.rd, self.reductor
+            enrichment_step += 1
+            local_problem_solves = self._enrich_once(U, mu, np.asarray(indicators)[:, 0], age_count)
 
 
 # ----------------------------------------------------------------------------------------------------------

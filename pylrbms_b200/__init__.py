@@ -18,3 +18,4 @@ from .reductor import LRBMSReductor, GenericRBSystemReductor, ExtensionError    
 from .reduced import ReducedModel, ReducedBlockOperator                               # noqa: F401
 
 __version__ = '0.1.0'
+from .online_enrichment import AdaptiveEnrichment, doerfler_marking                              # noqa: F401

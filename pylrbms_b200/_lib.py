@@ -22,6 +22,7 @@ EXPORTS = [
     'lrbms_symbolic_create', 'lrbms_symbolic_destroy', 'lrbms_symbolic_info', 'lrbms_symbolic_get',
     'lrbms_online_plan_create', 'lrbms_online_workspace_bytes', 'lrbms_online_solve', 'lrbms_online_estimate',
     'lrbms_online_sweep', 'lrbms_eta_max', 'lrbms_online_debug_timing',
+    'lrbms_pcg_workspace_bytes', 'lrbms_pcg_solve',
 ]
 
 VEC_ONE, VEC_UI, VEC_UN, VEC_UR = 0, 1, 2, 3
@@ -108,6 +109,8 @@ def load_library():
             'lrbms_online_sweep': (C.c_int, [vp, i64, vp, vp, vp, vp, vp, vp, vp, C.c_size_t, vp]),
             'lrbms_eta_max': (C.c_int, [vp, i64, vp, vp, vp, vp]),
             'lrbms_online_debug_timing': (C.c_int, [vp, vp, i32]),
+            'lrbms_pcg_workspace_bytes': (C.c_int, [vp, i64, P(C.c_size_t)]),
+            'lrbms_pcg_solve': (C.c_int, [vp, i32, vp, vp, vp, vp, vp, dbl, i32, P(i32), P(dbl), vp, C.c_size_t, vp]),
         }
         for name, (res, args) in protos.items():
             fn = getattr(lib, name)          # AttributeError here = header/library mismatch

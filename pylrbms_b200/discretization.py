@@ -61,6 +61,42 @@ class BlockSwipdgDiscretization:
         exactly as the reference does (``estimators.py:45-112``)."""
         return self.estimator.estimate(U, self.parse_parameter(mu), self, decompose=decompose)
 
+    def solve_for_local_correction(self, subdomain, Us, mu=None, inverse_options=None):
+        """Local corrector problem on the neighbourhood of ``subdomain`` (reference ``discretize...:227-316``).
+
+        The reference assembles the SWIPDG operator on the neighbourhood grid with dune-gdt, solves
+        ``(sum_q theta_q(mu) A_q^nbh) c = f^nbh`` (the current solution ``Us`` does not enter: its boundary functional is
+        commented out, ``:247-260``) and restricts ``c`` to the subdomain.  Assembly is outside the hot path, so here the
+        neighbourhood operator is the principal submatrix of the global block operator over the neighbourhood: the
+        one-sided coupling terms the diagonal blocks carry on the outer interfaces act as the weakly imposed homogeneous
+        Dirichlet condition of the oversampling problem.  The solve runs on the GPU (``lrbms_pcg_solve``);
+        ``inverse_options`` may hold ``{'rtol': ..., 'maxiter': ...}``.  ``Us`` is accepted for signature parity."""
+        import scipy.sparse as sp
+        import torch
+        from .kernels import DeviceCsr, pcg_solve
+        mu = self.parse_parameter(mu)
+        nb = list(self.neighborhoods[subdomain])
+        cache = self.__dict__.setdefault('_nbh_cache', {})
+        if subdomain not in cache:
+            mats = []
+            for op in self.operator.operators:
+                blocks = [[(op._blocks[k, l].csr.host if op._blocks[k, l] is not None else None) for l in nb] for k in nb]
+                mats.append(sp.bmat(blocks, format='csr'))
+            f = torch.cat([torch.from_numpy(self.rhs.operators[0]._array._blocks[k].to_numpy()[0]).cuda() for k in nb])
+            cache[subdomain] = (mats, f)
+        mats, f = cache[subdomain]
+        theta = [c.evaluate(mu) if hasattr(c, 'evaluate') else float(c) for c in self.operator.coefficients]
+        A = theta[0] * mats[0]
+        for q in range(1, len(mats)):
+            A = A + theta[q] * mats[q]
+        opts = dict(inverse_options or {})
+        x, iters, relres = pcg_solve(DeviceCsr(A.tocsr()), f, rtol=float(opts.get('rtol', 1e-12)), max_iter=opts.get('maxiter'))
+        self.last_local_correction_info = {'iterations': iters, 'relative_residual': relres, 'size': int(A.shape[0])}
+        sizes = [self.solution_space.subspaces[k].dim for k in nb]
+        start = int(np.sum(sizes[:nb.index(subdomain)]))
+        local = x[start:start + sizes[nb.index(subdomain)]]
+        return self.solution_space.subspaces[subdomain].from_data(local.cpu().numpy()[None, :])
+
     def shape_functions(self, subdomain, order=0):
         """reference ``discretize...:187-200``: constant 1, then x, y, x*y."""
         sf = self._shape_function_data[subdomain]

@@ -112,3 +112,24 @@ def project_once(csr, VL, VR, alpha=1.0):
     plan.run()
     plan.destroy()
     return out.cpu().numpy()
+
+
+def pcg_solve(csr, b, x0=None, rtol=1e-12, max_iter=None):
+    """Solve ``A x = b`` for a symmetric positive definite :class:`DeviceCsr` ``A`` with the Jacobi-preconditioned CG of
+    ``lrbms_pcg_solve``.  ``b`` / ``x0``: 1-D float64 CUDA tensors.  Returns ``(x, iterations, relative residual)``."""
+    import ctypes as C
+    torch = _torch()
+    n = csr.shape[0]
+    assert csr.shape[0] == csr.shape[1] == b.numel()
+    h = Handle.get()
+    x = torch.zeros(n, dtype=torch.float64, device='cuda') if x0 is None else x0.clone().contiguous()
+    nbytes = C.c_size_t()
+    h.check(h.lib.lrbms_pcg_workspace_bytes(h.h, n, C.byref(nbytes)))
+    ws = torch.empty(max(1, nbytes.value // 8), dtype=torch.float64, device='cuda')
+    iters, relres = C.c_int32(), C.c_double()
+    from ._lib import current_stream_ptr
+    h.check(h.lib.lrbms_pcg_solve(h.h, n, csr.rowptr.data_ptr(), csr.colind.data_ptr(), csr.values.data_ptr(),
+                                  b.contiguous().data_ptr(), x.data_ptr(), float(rtol),
+                                  int(max_iter if max_iter is not None else max(100, 10 * n)), C.byref(iters), C.byref(relres),
+                                  ws.data_ptr(), nbytes.value, current_stream_ptr()))
+    return x, iters.value, relres.value

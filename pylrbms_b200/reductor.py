@@ -115,11 +115,18 @@ class GenericRBSystemReductor:
         return np.concatenate([[0], np.cumsum([len(self.bases[s.id]) for s in subs])]).astype(np.int64)
 
     def reconstruct_local(self, u, space_id):
+        """pyMOR semantics ``RB[:u.dim].lincomb(u)``: a solution of an earlier reduced model stays reconstructible after the
+        basis was extended (the enrichment loop does exactly that, reference ``reductor.py:75-78``)."""
         k = self._sub_index[space_id]
-        offs = self._offsets()
+        dims = getattr(u, 'block_dims', None)
+        offs = np.concatenate([[0], np.cumsum(dims)]).astype(np.int64) if dims is not None else self._offsets()
         coeff = u.device_tensor[:, offs[k]:offs[k + 1]] if isinstance(u, ReducedVectorArray) else \
             np.atleast_2d(np.asarray(u.data if hasattr(u, 'data') else u))[:, offs[k]:offs[k + 1]]
-        return self.bases[space_id].lincomb(coeff)
+        basis = self.bases[space_id]
+        n = int(offs[k + 1] - offs[k])
+        if n < len(basis):
+            basis = basis[:n]
+        return basis.lincomb(coeff)
 
     def reconstruct(self, u):
         subs = self.d.solution_space.subspaces
