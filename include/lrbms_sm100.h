@@ -128,6 +128,26 @@ typedef struct {
 int lrbms_project_plan_create(lrbms_handle_t h, int32_t n_desc, const lrbms_project_desc_t* descs_host,
                               lrbms_plan_t* out);
 
+/* Incremental re-projection after an enrichment.  The reference re-runs the whole        */
+/* reductor.reduce() after every enrichment (online_enrichment.py:49-51); only the rows / columns that belong to the      */
+/* appended basis vectors change.  One descriptor assembles one new reduced block:                                       */
+/*   dst[r][c] = prev[row_map[r]][col_map[c]]                    both old                                                */
+/*             = cols_new[r][-col_map[c]-1]                      column c is new   (cols_new = alpha L^T A R[:, new])     */
+/*             = rows_new[c][-row_map[r]-1]                      row r is new      (rows_new = alpha R^T A^T L[:, new];   */
+/*                                                               rows_new == NULL: symmetric block, cols_new is used)    */
+typedef struct {
+  double* dst;             /* device, row-major NL x NR */
+  int32_t NL, NR;
+  const double* prev;      /* device, previous block, row-major with pNR columns (may be NULL if every row or column is new) */
+  int32_t pNR, n_cn;
+  const double* cols_new;  /* device, row-major NL x n_cn, or NULL when no column is new */
+  const double* rows_new;  /* device, row-major NR x n_rn, or NULL */
+  int32_t n_rn, reserved;
+  const int32_t* row_map;  /* device [NL] */
+  const int32_t* col_map;  /* device [NR] */
+} lrbms_remap_desc_t;
+int lrbms_remap_blocks(lrbms_handle_t h, int32_t n, const lrbms_remap_desc_t* descs_host, void* stream);
+
 /* run / destroy / introspect any plan */
 int lrbms_plan_run(lrbms_plan_t plan, void* stream);
 int lrbms_plan_destroy(lrbms_plan_t plan);

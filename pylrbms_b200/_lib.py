@@ -22,7 +22,7 @@ EXPORTS = [
     'lrbms_symbolic_create', 'lrbms_symbolic_destroy', 'lrbms_symbolic_info', 'lrbms_symbolic_get',
     'lrbms_online_plan_create', 'lrbms_online_workspace_bytes', 'lrbms_online_solve', 'lrbms_online_estimate',
     'lrbms_online_sweep', 'lrbms_eta_max', 'lrbms_online_debug_timing',
-    'lrbms_pcg_workspace_bytes', 'lrbms_pcg_solve',
+    'lrbms_pcg_workspace_bytes', 'lrbms_pcg_solve', 'lrbms_remap_blocks',
 ]
 
 VEC_ONE, VEC_UI, VEC_UN, VEC_UR = 0, 1, 2, 3
@@ -47,6 +47,12 @@ class ProjectDesc(C.Structure):
                 ('VR', C.c_void_p), ('ldr', C.c_int32), ('NR', C.c_int32),
                 ('out', C.c_void_p), ('ldo', C.c_int32),
                 ('alpha', C.c_double), ('symmetric', C.c_int32), ('reserved', C.c_int32)]
+
+
+class RemapDesc(C.Structure):
+    _fields_ = [('dst', C.c_void_p), ('NL', C.c_int32), ('NR', C.c_int32), ('prev', C.c_void_p), ('pNR', C.c_int32),
+                ('n_cn', C.c_int32), ('cols_new', C.c_void_p), ('rows_new', C.c_void_p), ('n_rn', C.c_int32),
+                ('reserved', C.c_int32), ('row_map', C.c_void_p), ('col_map', C.c_void_p)]
 
 
 class EstimatorTerm(C.Structure):
@@ -109,6 +115,7 @@ def load_library():
             'lrbms_online_sweep': (C.c_int, [vp, i64, vp, vp, vp, vp, vp, vp, vp, C.c_size_t, vp]),
             'lrbms_eta_max': (C.c_int, [vp, i64, vp, vp, vp, vp]),
             'lrbms_online_debug_timing': (C.c_int, [vp, vp, i32]),
+            'lrbms_remap_blocks': (C.c_int, [vp, i32, vp, vp]),
             'lrbms_pcg_workspace_bytes': (C.c_int, [vp, i64, P(C.c_size_t)]),
             'lrbms_pcg_solve': (C.c_int, [vp, i32, vp, vp, vp, vp, vp, dbl, i32, P(i32), P(dbl), vp, C.c_size_t, vp]),
         }

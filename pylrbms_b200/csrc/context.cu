@@ -114,6 +114,45 @@ int lrbms_plan_info(lrbms_plan_t plan, int32_t what, double* out) {
 }  // extern "C"
 
 // ------------------------------------------------------------------------------------------------------
+//  Incremental re-projection: assembly of the new reduced blocks from the previous ones and the narrow projections of
+//  the appended basis vectors (one CTA per block).
+// ------------------------------------------------------------------------------------------------------
+namespace {
+__global__ void remap_blocks_kernel(const lrbms_remap_desc_t* __restrict__ descs) {
+  const lrbms_remap_desc_t D = descs[blockIdx.x];
+  const int total = D.NL * D.NR;
+  for (int e = threadIdx.x; e < total; e += blockDim.x) {
+    const int r = e / D.NR, c = e - r * D.NR;
+    const int rm = D.row_map[r], cm = D.col_map[c];
+    double v;
+    if (cm < 0) v = D.cols_new[(int64_t)r * D.n_cn + (-cm - 1)];
+    else if (rm < 0) v = D.rows_new ? D.rows_new[(int64_t)c * D.n_rn + (-rm - 1)] : D.cols_new[(int64_t)c * D.n_cn + (-rm - 1)];
+    else v = D.prev[(int64_t)rm * D.pNR + cm];
+    D.dst[e] = v;
+  }
+}
+}  // namespace
+
+extern "C" int lrbms_remap_blocks(lrbms_handle_t h, int32_t n, const lrbms_remap_desc_t* descs_host, void* stream) {
+  LRBMS_REQUIRE(h, h && (n == 0 || descs_host) && n >= 0, "remap_blocks: bad argument");
+  if (n == 0) return LRBMS_OK;
+  LRBMS_CUDA_CHECK(h, cudaSetDevice(h->device));
+  for (int i = 0; i < n; ++i) {
+    const auto& d = descs_host[i];
+    LRBMS_REQUIRE(h, d.dst && d.row_map && d.col_map && d.NL >= 0 && d.NR >= 0, "remap_blocks: null pointer in descriptor");
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  lrbms_remap_desc_t* dd = nullptr;
+  LRBMS_CUDA_CHECK(h, cudaMallocAsync((void**)&dd, sizeof(lrbms_remap_desc_t) * n, s));
+  LRBMS_CUDA_CHECK(h, cudaMemcpyAsync(dd, descs_host, sizeof(lrbms_remap_desc_t) * n, cudaMemcpyHostToDevice, s));
+  LRBMS_CUDA_CHECK(h, cudaStreamSynchronize(s));        // descs_host may be released by the caller after return
+  remap_blocks_kernel<<<n, 256, 0, s>>>(dd);
+  LRBMS_CUDA_CHECK(h, cudaGetLastError());
+  LRBMS_CUDA_CHECK(h, cudaFreeAsync(dd, s));
+  return LRBMS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
 //  VectorArray kernels.  Arrays are dof-major (dim x ld); a "row" is one dof across all vectors, so every
 //  kernel walks rows with consecutive threads on consecutive vectors -> coalesced for ld == len.
 // ------------------------------------------------------------------------------------------------------

@@ -27,7 +27,10 @@ from __future__ import annotations
 
 import numpy as np
 
-from ._lib import Handle, make_project_plan, make_spmm_plan
+import ctypes as C
+
+from . import _lib
+from ._lib import Handle, current_stream_ptr, make_project_plan, make_spmm_plan, ptr
 from .distributed import exchange_regions, owner_rank, rank_and_world, region_layout
 from .kernels import project_desc, spmm_desc
 from .operators import (BlockColumnOperator, BlockEmbeddingOperator, BlockOperator, BlockProjectionOperator,
@@ -141,23 +144,45 @@ class GenericRBSystemReductor:
 # ----------------------------------------------------------------------------------------------------------
 
 class _ArrayRef:
-    """A dof-major device array seen by the kernels: pointer, row stride, number of vectors, number of dofs."""
-    __slots__ = ('ptr', 'ld', 'N', 'dim', 'keep', 'stage')
+    """A dof-major device array seen by the kernels: pointer, row stride, number of vectors, number of dofs.
 
-    def __init__(self, ptr, ld, N, dim, keep=None, stage=0):
+    ``key`` names the array across two plans of one reductor and ``labels`` says what every column *is* -- row ``c`` is
+    ``(k, q, a)``: image under the q-th affine component (0 for the basis itself and its Oswald image) of basis vector
+    ``a`` of subdomain ``k``; ``k = -1`` marks data that never changes (right-hand sides).  Incremental re-projection
+     uses both to tell old columns from the ones an enrichment appended."""
+    __slots__ = ('ptr', 'ld', 'N', 'dim', 'keep', 'stage', 'key', 'labels')
+
+    def __init__(self, ptr, ld, N, dim, keep=None, stage=0, key=None, labels=None):
         self.ptr, self.ld, self.N, self.dim, self.keep = int(ptr), int(ld), int(N), int(dim), keep
         self.stage = stage        # SpMM stage that produces the data (0: bases and their OI / RT images)
+        self.key = key if key is not None else ('static', int(ptr), int(ld), int(N))
+        self.labels = labels if labels is not None else \
+            np.stack([np.full(int(N), -1), np.zeros(int(N), dtype=np.int64), np.arange(int(N))], axis=1).astype(np.int64)
 
     @staticmethod
     def of(arr):
-        return _ArrayRef(arr.device_ptr, arr.ld, len(arr), arr.dim, arr)
+        return _ArrayRef(arr.device_ptr, arr.ld, len(arr), arr.dim, arr, key=getattr(arr, '_plan_key', None),
+                         labels=getattr(arr, '_plan_labels', None))
+
+
+def _labels(k, qs, n):
+    """Column labels ``(k, q, a)`` in q-major order for ``n`` basis vectors of subdomain ``k``."""
+    qs = list(qs)
+    return np.stack([np.full(len(qs) * n, k), np.repeat(qs, n), np.tile(np.arange(n), len(qs))], axis=1).astype(np.int64)
 
 
 class _Planner:
     """Collects SpMM stages and projection jobs for one ``reduce()``; owns the reduced output buffer."""
 
-    def __init__(self, handle, owner_rank_of=None, rank=0, world=1):
+    def __init__(self, handle, owner_rank_of=None, rank=0, world=1, prev=None):
         self.h = handle
+        # incremental re-projection: the previous plan of this reductor (its output buffer holds every old entry) and the
+        # basis sizes it was built for; None -> everything is projected from scratch
+        self.prev = prev
+        self.N_old = list(prev.block_dims) if prev is not None else None
+        self.job_index = {}            # job key -> (token, L labels, R labels)
+        self.inc_jobs = []             # jobs that exist in the previous plan: only new rows / columns are computed
+        self.gathers, self.scatters = [], []
         self.jobs = []                 # (owner, csr|None, n_rows, L ref, R ref, out offset, ldo, alpha)
         self.spmm_stages = [[]]
         self._spmm_cache = {}
@@ -199,7 +224,7 @@ class _Planner:
         stage = V.stage + 1
         ld = max(4, (V.N + 3) // 4 * 4)
         W = self._scratch(max(1, csr.shape[0]), ld)
-        ref = _ArrayRef(W.data_ptr(), ld, V.N, csr.shape[0], W, stage)
+        ref = _ArrayRef(W.data_ptr(), ld, V.N, csr.shape[0], W, stage, key=('spmm', id(csr), V.key), labels=V.labels)
         while len(self.spmm_stages) <= stage:
             self.spmm_stages.append([])
         if self.mine(owner):
@@ -211,12 +236,139 @@ class _Planner:
     def project(self, owner, csr, L, R, alpha=1.0):
         """Schedule ``alpha * L^T csr R`` (``csr=None``: identity); returns the output token (row-major ``L.N x R.N``)."""
         token = self.alloc(owner, L.N * R.N)
+        key = (id(csr) if csr is not None else None, L.key, R.key, float(alpha))
+        self.job_index[key] = (token, L.labels, R.labels)
         if L.N and R.N and self.mine(owner):
             n_rows = csr.shape[0] if csr is not None else L.dim
-            sym = (L.ptr == R.ptr and L.ld == R.ld and L.N == R.N and L.N > 40 and (csr is None or csr.symmetric))
-            self.jobs.append((token, csr, n_rows, L, R, R.N, alpha, sym))
+            sym = (L.ptr == R.ptr and L.ld == R.ld and L.N == R.N and (csr is None or csr.symmetric))
+            if self.prev is not None and key in self.prev.job_index:
+                self.inc_jobs.append((token, csr, n_rows, L, R, alpha, sym, key))
+            else:
+                self.jobs.append((token, csr, n_rows, L, R, R.N, alpha, sym and L.N > 40))
         self.keep += [csr, L.keep, R.keep]
         return token
+
+    # -- incremental jobs ------------------------------------------------------------------------------------------
+    def _is_new(self, labels):
+        k, a = labels[:, 0], labels[:, 2]
+        n_old = np.asarray(self.N_old + [0], dtype=np.int64)        # k = -1 (static data) -> index -1 -> 0, never new
+        return (k >= 0) & (a >= n_old[k])
+
+    def _gather_ref(self, ref, cols):
+        """A compact copy of columns ``cols`` of ``ref`` (cached per array), filled at run time -- after the SpMM stages
+        that produce ``ref`` -- by one ``lrbms_va_copy_cols`` launch."""
+        if ref.key in self._gather_cache:
+            return self._gather_cache[ref.key]
+        torch = _torch()
+        n = len(cols)
+        ld = max(4, (n + 3) // 4 * 4)
+        buf = torch.zeros((max(1, ref.dim), ld), dtype=torch.float64, device='cuda')
+        idx = np.ascontiguousarray(cols, dtype=np.int32)
+        src_ptr, src_ld, dim, h = ref.ptr, ref.ld, ref.dim, self.h
+
+        def run():
+            for c0 in range(0, n, 256):
+                cnt = min(256, n - c0)
+                chunk = np.ascontiguousarray(idx[c0:c0 + cnt])
+                h.check(h.lib.lrbms_va_copy_cols(h.h, dim, cnt, ptr(chunk), src_ptr, src_ld, buf.data_ptr(), ld, c0,
+                                                 current_stream_ptr()))
+        if dim and n:
+            self.gathers.append(run)
+        out = _ArrayRef(buf.data_ptr(), ld, n, ref.dim, [buf, ref.keep])
+        self._gather_cache[ref.key] = out
+        return out
+
+    @staticmethod
+    def _codes(labels):
+        """One sortable integer per column label ``(k, q, a)``."""
+        return ((labels[:, 0] + 1) * 64 + labels[:, 1]) * (1 << 20) + labels[:, 2]
+
+    def _plan_incremental(self, base, descs):
+        """Turn every incremental job into (at most) two narrow projections plus one entry of the block-remap launch:
+
+            G[old, old]  <- the previous plan's output
+            G[:, new]     = alpha L^T A R[:, new]                             (all rows x new columns)
+            G[new, old]   = (alpha R^T A^T L[:, new])^T restricted to old     (new rows; from G[:, new]^T if symmetric)
+        """
+        torch = _torch()
+        prev = self.prev
+        self._gather_cache = {}
+        todo, maps, tmp_sizes = [], [], []
+        map_cache = {}
+
+        def col_map(ref, plabels):
+            """``[N]`` int32: index in the previous array for old columns, ``-(1 + rank among the new ones)`` for new ones;
+            None if an old column is missing from the previous array."""
+            ck = (ref.key, id(plabels))
+            if ck not in map_cache:
+                new = self._is_new(ref.labels)
+                m = np.empty(ref.N, dtype=np.int32)
+                m[new] = -1 - np.arange(int(new.sum()), dtype=np.int32)
+                old_codes = self._codes(ref.labels[~new])
+                pc = self._codes(plabels)
+                order = np.argsort(pc, kind='stable')
+                pos = np.searchsorted(pc[order], old_codes)
+                ok = len(pc) > 0 or len(old_codes) == 0
+                if ok and len(old_codes):
+                    pos = np.minimum(pos, len(pc) - 1)
+                    ok = bool(np.all(pc[order][pos] == old_codes))
+                if ok and len(old_codes):
+                    m[~new] = order[pos].astype(np.int32)
+                map_cache[ck] = (m, np.nonzero(new)[0]) if ok else None
+            return map_cache[ck]
+
+        for (token, csr, n_rows, L, R, alpha, sym, key) in self.inc_jobs:
+            ptoken, pL, pR = prev.job_index[key]
+            rm, cm = col_map(L, pL), col_map(R, pR)
+            if rm is None or cm is None:
+                # an "old" column the previous plan did not have: project this block from scratch
+                self.jobs.append((token, csr, n_rows, L, R, R.N, alpha, sym and L.N > 40))
+                continue
+            (row_map, rows_new), (cmap, cols_new) = rm, cm
+            n_cn, n_rn = len(cols_new), len(rows_new)
+            need_rows = n_rn > 0 and n_cn < R.N and not sym
+            todo.append((token, ptoken, L.N, R.N, len(pR), n_cn, n_rn if need_rows else 0, len(maps), len(maps) + 1,
+                         len(tmp_sizes), len(tmp_sizes) + 1))
+            maps += [row_map, cmap]
+            tmp_sizes += [L.N * n_cn, R.N * n_rn if need_rows else 0]
+            if n_cn:
+                Rn = self._gather_ref(R, cols_new)
+                descs.append((csr, n_rows, L, Rn, len(tmp_sizes) - 2, alpha))
+            if need_rows:
+                Ln = self._gather_ref(L, rows_new)
+                csr_t = csr.T if csr is not None else None
+                descs.append((csr_t, csr_t.shape[0] if csr_t is not None else R.dim, R, Ln, len(tmp_sizes) - 1, alpha))
+                self.keep.append(csr_t)
+        # one buffer for every narrow projection result, one for every index map
+        tmp_off = np.concatenate([[0], np.cumsum(tmp_sizes)]).astype(np.int64)
+        tmp = torch.zeros(max(1, int(tmp_off[-1])), dtype=torch.float64, device='cuda')
+        map_off = np.concatenate([[0], np.cumsum([len(m) for m in maps])]).astype(np.int64)
+        maps_dev = torch.from_numpy(np.concatenate(maps) if maps else np.zeros(1, dtype=np.int32)).cuda()
+        real = []
+        for d_ in descs:
+            if isinstance(d_, tuple):
+                csr, n_rows, L, R, slot, alpha = d_
+                real.append(project_desc(csr, n_rows, L.ptr, L.ld, L.N, R.ptr, R.ld, R.N, tmp.data_ptr() + 8 * int(tmp_off[slot]),
+                                         R.N, alpha))
+            else:
+                real.append(d_)
+        descs[:] = real
+        remap = (_lib.RemapDesc * max(1, len(todo)))()
+        out_ptr, prev_ptr, tp, mp = self.out.data_ptr(), prev.out.data_ptr(), tmp.data_ptr(), maps_dev.data_ptr()
+        for n, (token, ptoken, NL, NR, pNR, n_cn, n_rn, mr, mc, t1, t2) in enumerate(todo):
+            r = remap[n]
+            r.dst, r.NL, r.NR = out_ptr + 8 * int(self.offsets[token]), NL, NR
+            r.prev, r.pNR = prev_ptr + 8 * int(prev.offsets[ptoken]), pNR
+            r.n_cn, r.cols_new = n_cn, (tp + 8 * int(tmp_off[t1])) if n_cn else None
+            r.n_rn, r.rows_new = n_rn, (tp + 8 * int(tmp_off[t2])) if n_rn else None
+            r.row_map, r.col_map = mp + 4 * int(map_off[mr]), mp + 4 * int(map_off[mc])
+        n_remap, h = len(todo), self.h
+
+        def scatter():
+            if n_remap:
+                h.check(h.lib.lrbms_remap_blocks(h.h, n_remap, C.cast(remap, C.c_void_p), current_stream_ptr()))
+        self.scatters.append(scatter)
+        self.keep += [tmp, maps_dev, remap]
 
     def finalize(self):
         """Allocate the output buffer, resolve tokens to offsets, create the plans."""
@@ -226,6 +378,8 @@ class _Planner:
         self.out = torch.zeros(max(1, int(starts[-1])), dtype=torch.float64, device='cuda')
         base = self.out.data_ptr()
         descs = []
+        if self.inc_jobs:
+            self._plan_incremental(base, descs)
         for (token, csr, n_rows, L, R, ldo, alpha, sym) in self.jobs:
             descs.append(project_desc(csr, n_rows, L.ptr, L.ld, L.N, R.ptr, R.ld, R.N, base + 8 * int(self.offsets[token]),
                                       ldo, alpha, symmetric=sym))
@@ -233,12 +387,24 @@ class _Planner:
         self.project_plan = make_project_plan(self.h, descs, []) if descs else None
         self.n_project_descs = len(descs)
         self.n_spmm_descs = sum(len(st) for st in self.spmm_stages)
+        self.n_incremental_jobs = len(self.inc_jobs)
 
     def run(self):
         for p in self.spmm_plans:
             p.run()
+        for g in self.gathers:
+            g()
         if self.project_plan is not None:
             self.project_plan.run()
+        for sc in self.scatters:
+            sc()
+
+    def release_previous(self):
+        """Drop the reference to the previous plan once this plan's results are complete (no chain of old plans)."""
+        if self.inc_jobs:
+            self.rerunnable = False          # the copies from the previous plan cannot be repeated
+        self.prev = None
+        self.gathers, self.scatters = [], []
 
     def exchange(self):
         """Multi-GPU: every rank broadcasts its contiguous result region (an all-gather of disjoint reduced blocks)."""
@@ -270,8 +436,11 @@ def _gather_columns(planner, arrays):
     adjacent = all(a.ld == arrays[0].ld for a in arrays) and all(
         arrays[k + 1].device_ptr == arrays[k].device_ptr + 8 * len(arrays[k]) for k in range(len(arrays) - 1))
     total = sum(len(a) for a in arrays)
+    refs = [_ArrayRef.of(a) for a in arrays]
+    key = ('cat',) + tuple(r.key for r in refs)
+    labels = np.concatenate([r.labels for r in refs], axis=0)
     if adjacent:
-        return _ArrayRef(arrays[0].device_ptr, arrays[0].ld, total, arrays[0].dim, arrays)
+        return _ArrayRef(arrays[0].device_ptr, arrays[0].ld, total, arrays[0].dim, arrays, key=key, labels=labels)
     if any(getattr(a, '_is_view', False) for a in arrays):
         # slab views are filled by the plan's first SpMM stage, i.e. after planning: copying them now would copy zeros
         raise NotImplementedError('image bases of one neighbourhood must be adjacent column slices of one slab')
@@ -280,6 +449,7 @@ def _gather_columns(planner, arrays):
     for a in arrays:
         cat._copy_cols_from(a, None, pos)
         pos += len(a)
+    cat._plan_key, cat._plan_labels = key, labels
     return _ArrayRef.of(cat)
 
 
@@ -406,6 +576,7 @@ class LRBMSReductor(GenericRBSystemReductor):
         self.num_cpus = num_cpus            # accepted and ignored, like the reference (reductor.py:19,84)
         self.shard = bool(shard)
         self.reuse_plan = False
+        self.incremental = False            # reduce() after an enrichment projects only the new rows / columns (8f rank 2)
         super().__init__(d, bases=bases, products=products)
         if order is None and bases is None:
             order = 0
@@ -418,16 +589,25 @@ class LRBMSReductor(GenericRBSystemReductor):
     def _shard_info(self):
         return rank_and_world() if self.shard else (0, 1)
 
-    def build_plan(self):
-        """Plan the whole offline projection for the current bases (no kernel runs yet)."""
+    def build_plan(self, incremental=False):
+        """Plan the whole offline projection for the current bases (no kernel runs yet).
+
+        ``incremental=True``: the previous plan of this reductor is taken as the source of
+        every reduced entry whose row *and* column belong to basis vectors that already existed; only the rows / columns
+        of vectors appended since (``extend_basis_local``) are projected, and only their Oswald / flux-reconstruction
+        images are computed.  The reference re-projects everything after each enrichment (``online_enrichment.py:49-51``)."""
         torch = _torch()
         d = self.d
         subs = d.solution_space.subspaces
         S = len(subs)
         rank, world = self._shard_info()
         owner_rank_of = (lambda owner: owner_rank(owner, S, world)) if world > 1 else None
-        planner = _Planner(Handle.get(), owner_rank_of, rank, world)
         old = self.last_plan
+        prev = None
+        if incremental and world == 1 and old is not None and getattr(old, 'reusable', False) and \
+                all(len(self.bases[s.id]) >= n for s, n in zip(subs, old.block_dims)):
+            prev = old
+        planner = _Planner(Handle.get(), owner_rank_of, rank, world, prev=prev)
         if old is not None and getattr(old, 'reusable', False):
             # the reduced model of the previous plan is no longer referenced: recycle its scratch arrays
             pool = {}
@@ -435,7 +615,11 @@ class LRBMSReductor(GenericRBSystemReductor):
                 pool.setdefault(key, []).append(t)
             planner.scratch_pool = pool
         N = [len(self.bases[s.id]) for s in subs]
+        for k, sp_ in enumerate(subs):                          # what the columns of every basis are (see _ArrayRef)
+            self.bases[sp_.id]._plan_key = ('V', k)
+            self.bases[sp_.id]._plan_labels = _labels(k, [0], N[k])
         V = [_ArrayRef.of(self.bases[s.id]) for s in subs]
+        N_old = prev.block_dims if prev is not None else [0] * S
 
         # ---- Oswald-interpolation and flux-reconstruction images of the bases (reference reductor.py:36-60), written
         #      into per-target-subdomain slabs: slab_i = [component i of bases['OI_k']]_{k in N(i)}
@@ -460,22 +644,34 @@ class LRBMSReductor(GenericRBSystemReductor):
         for k in range(S):
             oi_k = oi._blocks[k, k]
             comps_o, comps_r = [], []
+            n0, n1 = N_old[k], N[k]                               # columns [0, n0) exist in the previous plan's slabs
             for c, i in enumerate(nbh[k]):
                 view_o = oi_slab[i][:, oi_col[i][k]:oi_col[i][k] + N[k]]
-                comps_o.append(oi_k.range.subspaces[c].from_dofmajor(view_o, N[k]))
-                if N[k] and planner.mine(i):
-                    planner.spmm_stages[0].append(spmm_desc(oi_k.components[c], V[k].ptr, V[k].ld, N[k],
-                                                            view_o.data_ptr(), oi_slab[i].stride(0)))
+                arr_o = oi_k.range.subspaces[c].from_dofmajor(view_o, N[k])
+                arr_o._plan_key, arr_o._plan_labels = ('oi', i, k), _labels(k, [0], N[k])
+                comps_o.append(arr_o)
+                if prev is not None and n0:
+                    pc = prev.oi_col[i][k]
+                    view_o[:, :n0] = prev.oi_slab[i][:, pc:pc + n0]
+                if n1 > n0 and planner.mine(i):
+                    planner.spmm_stages[0].append(spmm_desc(oi_k.components[c], V[k].ptr + 8 * n0, V[k].ld, n1 - n0,
+                                                            view_o.data_ptr() + 8 * n0, oi_slab[i].stride(0)))
                 view_r = rt_slab[i][:, rt_col[i][k]:rt_col[i][k] + Q * N[k]]
                 rt_space = fr.operators[0]._blocks[k, k].range.subspaces[c]
-                comps_r.append(rt_space.from_dofmajor(view_r, Q * N[k]))
+                arr_r = rt_space.from_dofmajor(view_r, Q * N[k])
+                arr_r._plan_key, arr_r._plan_labels = ('rt', i, k), _labels(k, range(Q), N[k])
+                comps_r.append(arr_r)
                 for q in range(Q):                               # q-major ordering of the RT basis (reductor.py:55-60)
                     fr_kq = fr.operators[q]._blocks[k, k]
-                    if N[k] and planner.mine(i):
-                        planner.spmm_stages[0].append(spmm_desc(fr_kq.components[c], V[k].ptr, V[k].ld, N[k],
-                                                                view_r.data_ptr() + 8 * q * N[k], rt_slab[i].stride(0)))
+                    if prev is not None and n0:
+                        pc = prev.rt_col[i][k] + q * n0
+                        view_r[:, q * n1:q * n1 + n0] = prev.rt_slab[i][:, pc:pc + n0]
+                    if n1 > n0 and planner.mine(i):
+                        planner.spmm_stages[0].append(spmm_desc(fr_kq.components[c], V[k].ptr + 8 * n0, V[k].ld, n1 - n0,
+                                                                view_r.data_ptr() + 8 * (q * n1 + n0), rt_slab[i].stride(0)))
             self.bases[oi.range.subspaces[k].id] = BlockVectorArray(comps_o, oi.range.subspaces[k])
             self.bases[fr.range.subspaces[k].id] = BlockVectorArray(comps_r, fr.range.subspaces[k])
+        planner.oi_slab, planner.rt_slab, planner.oi_col, planner.rt_col = oi_slab, rt_slab, oi_col, rt_col
         planner.keep += [oi_slab, rt_slab]
 
         # ---- every operator and product of the discretization (reference reductor.py:70 -> GenericRBSystemReductor._reduce)
@@ -501,15 +697,17 @@ class LRBMSReductor(GenericRBSystemReductor):
     def _reduce(self):
         d = self.d
         key = self._plan_key()
-        if self.reuse_plan and self.last_plan is not None and getattr(self, '_last_key', None) == key:
+        if self.reuse_plan and self.last_plan is not None and getattr(self, '_last_key', None) == key and \
+                getattr(self.last_plan, 'rerunnable', True):
             # same basis buffers and sizes as last time: the plan is still valid.  Opt-in, because the reduced model
             # returned earlier shares the plan's output buffer and is overwritten by this run.
             planner = self.last_plan
         else:
-            planner = self.build_plan()
+            planner = self.build_plan(incremental=self.incremental)
             self._last_key = key
         planner.run()
         planner.exchange()
+        planner.release_previous()
         planner.reusable = True       # its SpMM scratch may be recycled by the next plan of this reductor (same stream)
         N = planner.block_dims
         fr = d.estimator.flux_reconstruction

@@ -276,3 +276,52 @@ def test_error_behaviour(handle):
     w = torch.zeros(64, dtype=torch.uint8, device='cuda')
     rc = plan.handle.lib.lrbms_online_solve(plan.p, 1, ptr(theta), ptr(u), ptr(info), ptr(w), 64, current_stream_ptr())
     assert rc == -1 and b'workspace too small' in plan.handle.lib.lrbms_last_error(plan.handle.h)
+
+
+@pytest.mark.parametrize('num_subdomains,cells,basis_size', [((3, 2), 4, [3, 5, 4, 6, 5, 4]), ((2, 2, 2), (2, 2, 2), 5)])
+def test_incremental_reprojection_matches_full(handle, num_subdomains, cells, basis_size):
+    """after an enrichment only the rows / columns of the appended basis vectors are
+    projected; everything else is taken from the previous plan.  The result must equal a from-scratch projection of the
+    same bases (the reference's behaviour, ``online_enrichment.py:49-51``) and the oracle's."""
+    from pylrbms_b200 import LRBMSReductor, discretize
+    data, d_ref, red_ref, d, red = _setup(num_subdomains, cells, basis_size, 21)
+    S = data.num_subdomains
+    rng = np.random.default_rng(3)
+    # extend in the local energy product, as the reference does (scripts/online_adaptive_lrbms.py:107): the given bases are
+    # orthonormal in it, which is what makes the Gram-Schmidt result independent of the order of the projections
+    red.products = [d.operators['local_energy_dg_product_%d' % k] for k in range(S)]
+    red_ref.products = [d_ref.operators['local_energy_dg_product_%d' % k] for k in range(S)]
+    red.incremental = True
+    rd0 = red.reduce()
+    assert red.last_plan.n_incremental_jobs == 0
+    flops_full = red.last_plan.stats()['flops']
+    for step, enriched in enumerate(([1], [0, S - 1], list(range(S)))):      # one, two, all subdomains; twice the same one
+        for k in enriched:
+            sid = 'domain_%d' % k
+            new = rng.standard_normal((1 + (k + step) % 2, int(data.n[k])))
+            red.extend_basis_local(d.solution_space.subspaces[k].from_data(new))
+            red_ref.extend_basis_local(d_ref.solution_space.subspaces[k].make_array(new))
+        rd = red.reduce()
+        plan = red.last_plan
+        assert plan.n_incremental_jobs > 0
+        if len(enriched) < S:
+            assert plan.stats()['flops'] < 0.8 * flops_full
+        # from-scratch projection of the same bases through a fresh reductor
+        bases_now = {'domain_%d' % k: red.bases['domain_%d' % k].to_numpy() for k in range(S)}
+        rd_full = LRBMSReductor(d, bases=bases_now).reduce()
+        rd_ref = red_ref.reduce()
+        for name in list(d.operators) + list(d.products):
+            got = _blockwise(rd.operators[name] if name in rd.operators else rd.products[name])
+            full = _blockwise(rd_full.operators[name] if name in rd_full.operators else rd_full.products[name])
+            ref = _blockwise_ref(red_ref, name)
+            scale = max(np.abs(v).max() for v in ref.values())
+            assert set(got) == set(full)
+            for key, B in full.items():
+                assert np.abs(got[key] - B).max() <= RTOL * scale, '{} block {} (incremental vs full)'.format(name, key)
+            for key, B in ref.items():
+                assert np.abs(got[key] - B).max() <= RTOL * scale, '{} block {} (incremental vs oracle)'.format(name, key)
+        mus = np.linspace(data.parameter_range[0], data.parameter_range[1], 4)
+        U, eta, _, _ = rd.sweep(mus, decompose=True)
+        U2, eta2, _, _ = rd_full.sweep(mus, decompose=True)
+        assert np.abs(U.data - U2.data).max() <= 1e-9 * np.abs(U2.data).max()
+        assert np.abs(eta - eta2).max() <= 1e-9 * np.abs(eta2).max()
