@@ -38,11 +38,10 @@ METRIC = 'online reduced solves+estimates/s (mu-batched)'
 UNIT = 'solves+estimates/s'
 
 # DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed `ncu --set full` captures
-# of the default workload (profiles/r01_final_ncu_full_*_raw.csv); null for any other workload.
+# of the default workload (profiles/r01b_ncu_full_*_raw.csv); null for any other workload.
 NCU_TRAFFIC_BYTES = {
-    'solve_kernel_v2': 11.743e9 + 16.449e9,           # 10 000 parameters per launch
-    'projection_plan': (0.0755 + 0.5789 + 0.4077 + 1.2004 + 0.2934 + 0.2211 + 2.0698 + 1.3553) * 1e9 +
-                       (0.0030 + 0.0079 + 0.0154 + 0.0188 + 0.0048 + 0.0073 + 0.0917 + 2.4280) * 1e9,   # 7 project + 1 spmm launch
+    'solve_kernel_v2': 11.939e9 + 16.443e9,           # 10 000 parameters per launch
+    'projection_plan': 7.213e9 + 2.785e9,             # the 15 launches of one plan run: 6 spmm + 4 project + 5 gram kernels
 }
 
 
