@@ -345,6 +345,36 @@ def run_b200(a):
             'launches_per_reduce': st['launches'], 'roofline': roof,
             'first_reduce_incl_planning_s': t_reduce_first,
         }
+    # ---- N > 1: the subdomain-sharded offline half (strong scaling: the same operator set split over the ranks, each rank
+    #      projects the blocks of its strip of subdomains; the reduced regions are exchanged over NCCL afterwards)
+    if world > 1 and offline is not None:
+        red_s = LRBMSReductor(d, bases=bases, shard=True)
+        red_s.reduce()
+        ps = red_s.last_plan
+        for _ in range(3):
+            ps.run(); ps.exchange()
+        t_run, t_all = [], []
+        for _ in range(max(3, a.steps)):
+            flush_l2()
+            barrier()
+            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            e0.record()
+            ps.run()
+            e1.record()
+            ps.exchange()
+            e2.record()
+            e2.synchronize()
+            t_run.append(e0.elapsed_time(e1)); t_all.append(e0.elapsed_time(e2))
+        tt = torch.tensor([float(np.mean(t_run)), float(np.mean(t_all))], dtype=torch.float64, device='cuda')
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        offline['sharded'] = {
+            'n_gpus': world, 'scaling': 'strong', 'partition': 'contiguous strips of subdomains per rank',
+            'ms_all_stages_max_over_ranks': float(tt[0].item()), 'ms_with_exchange_max_over_ranks': float(tt[1].item()),
+            'ms_all_stages_1gpu_unsharded_this_rank': offline['ms_all_stages'],
+            'speedup_vs_unsharded': offline['ms_all_stages'] / float(tt[0].item()),
+            'exchange': 'one NCCL broadcast per rank region (all-gather of disjoint reduced blocks), %d doubles in total' % int(ps.out.numel()),
+            'projection_descriptors_this_rank': ps.n_project_descs,
+        }
     if a.synthetic3d:
         # auxiliary measurement (config C4 shape): the offline half only; the driver's bench line is the default workload
         if rank == 0:
