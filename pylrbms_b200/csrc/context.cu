@@ -56,6 +56,15 @@ int lrbms_create(int device, lrbms_handle_t* out) {
                           "; this library is built for sm_100a only");
   e = cudaSetDevice(device);
   if (e != cudaSuccess) return lrbms_fail(nullptr, LRBMS_ERR_CUDA, cudaGetErrorString(e));
+  {
+    // keep freed plan memory in the default pool (see plan_alloc)
+    cudaMemPool_t pool = nullptr;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess && pool) {
+      unsigned long long keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    cudaGetLastError();
+  }
   lrbms_context* ctx = new lrbms_context();
   ctx->device = device;
   ctx->sm_count = prop.multiProcessorCount;
@@ -91,7 +100,9 @@ int lrbms_plan_run(lrbms_plan_t plan, void* stream) {
 
 int lrbms_plan_destroy(lrbms_plan_t plan) {
   if (!plan) return LRBMS_OK;
-  for (void* p : plan->device_allocs) cudaFree(p);
+  // the plan's buffers go back to the pool in stream order; work that still uses them may sit on any stream
+  if (!plan->device_allocs.empty()) cudaDeviceSynchronize();
+  for (void* p : plan->device_allocs) cudaFreeAsync(p, (cudaStream_t)0);
   delete plan;
   return LRBMS_OK;
 }
