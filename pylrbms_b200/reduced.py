@@ -505,11 +505,28 @@ class ReducedModel:
         th_pin, th_dev, u, eta, info = bufs
         th_pin.copy_(torch.from_numpy(th))
         th_dev.copy_(th_pin, non_blocking=True)
-        self.sweep_device(th_dev, u, eta, info=info)
-        u_host.copy_(u, non_blocking=True)
-        eta_host.copy_(eta, non_blocking=True)
-        bad = int((info != 0).sum().item())          # synchronises the stream: the copies above are complete
-        torch.cuda.current_stream().synchronize()
+        # The batch goes through in (up to) four chunks so that the device->host copy of one chunk's solutions overlaps
+        # the kernels of the next; chunks are multiples of the persistent solve grid (one parameter per CTA and round).
+        grid = max(1, self.online_plan.handle.sm_count)
+        chunk = n_mu
+        if n_mu >= 32 * grid:
+            chunk = ((n_mu + 3) // 4 + grid - 1) // grid * grid
+        copy_stream = self._work.get('copy_stream')
+        if copy_stream is None:
+            copy_stream = self._work['copy_stream'] = torch.cuda.Stream()
+        main = torch.cuda.current_stream()
+        for lo in range(0, n_mu, chunk):
+            hi = min(n_mu, lo + chunk)
+            self.sweep_device(th_dev[lo:hi], u[lo:hi], eta[lo:hi], info=info[lo:hi])
+            ev = torch.cuda.Event()
+            ev.record(main)
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(ev)
+                u_host[lo:hi].copy_(u[lo:hi], non_blocking=True)
+                eta_host[lo:hi].copy_(eta[lo:hi], non_blocking=True)
+        bad = int((info != 0).sum().item())          # synchronises the compute stream
+        copy_stream.synchronize()                    # ... and the copies
+        main.wait_stream(copy_stream)
         return bad
 
     def sweep_sharded(self, mus):
