@@ -180,6 +180,8 @@ class _Planner:
         # basis sizes it was built for; None -> everything is projected from scratch
         self.prev = prev
         self.N_old = list(prev.block_dims) if prev is not None else None
+        self.narrow_left = True        # L^T A R with a narrow L and a wide R is computed as (A^T L)^T R
+        self.fuse_cache = None         # {ids of the chained matrices: (fused CsrOperator, keepalive)}; None: chains are not fused
         self.job_index = {}            # job key -> (token, L labels, R labels)
         self.inc_jobs = []             # jobs that exist in the previous plan: only new rows / columns are computed
         self.gathers, self.scatters = [], []
@@ -547,6 +549,21 @@ def _plan_chain(op, bases, planner, owner, name):
         chain = chain[1:]
     if not all(isinstance(m, CsrOperator) for m in chain):
         raise NotImplementedError('{}: only sparse matrices may sit between the selections'.format(op.name))
+    # ---- several sparse matrices in a row (r_dd: D^T M D): their product is formed once on the host and cached for the
+    #      life of the reductor -- the operators are static -- so the chain costs one SpMM and, for r_dd, a Gram over the
+    #      m_i flux dofs instead of the n_i DG dofs.  Same result up to the order of summation.
+    if len(chain) >= 2 and planner.fuse_cache is not None:
+        key = tuple(id(m.csr) for m in chain)
+        if key not in planner.fuse_cache:
+            from .kernels import DeviceCsr
+            P = chain[0].csr.host
+            for m in chain[1:]:
+                P = P @ m.csr.host
+            P = P.tocsr()
+            P.sort_indices()
+            planner.fuse_cache[key] = (CsrOperator(DeviceCsr(P), source_id=chain[-1].source.id, range_id=chain[0].range.id,
+                                                   name='fused_chain'), [m.csr for m in chain])
+        chain = [planner.fuse_cache[key][0]]
     # ---- (A^T ...)-prefix: L^T A^T = (A L)^T, one SpMM on the left array (shared with the right side through the cache)
     while len(chain) > 1 and chain[0].transposed_of is not None:
         L = planner.spmm(owner, chain[0].transposed_of.csr, L)
@@ -556,6 +573,11 @@ def _plan_chain(op, bases, planner, owner, name):
         R = planner.spmm(owner, chain[-1].csr, R)
         chain = chain[:-1]
     csr = chain[0].csr if chain else None
+    if csr is not None and planner.narrow_left and (L.N > 40 or R.N > 40) and 2 * L.N <= R.N:
+        # too wide for the fused kernel, and the left side is the narrow one: L^T A R = (A^T L)^T R.  One narrow SpMM on
+        # the left array instead of a scratch SpMM over all columns of R (df_ab: 20 instead of 200 columns, r_fd: 1)
+        L = planner.spmm(owner, csr.T, L)
+        csr = None
     token = planner.project(owner, csr, L, R)
     rdims = [1] if functional else _dims(op.range, bases)
     return ReducedBlockOperator(planner, [SuperBlock(row_idx, col_idx, token, sum(row_sizes), sum(col_sizes),
@@ -576,6 +598,8 @@ class LRBMSReductor(GenericRBSystemReductor):
         self.num_cpus = num_cpus            # accepted and ignored, like the reference (reductor.py:19,84)
         self.shard = bool(shard)
         self.reuse_plan = False
+        self.fuse_chains = True             # products of consecutive sparse matrices in an operator chain are formed once (host)
+        self.narrow_left = True             # chains with a narrow left and a wide right side apply the matrix to the left side
         self.incremental = False            # reduce() after an enrichment projects only the new rows / columns (8f rank 2)
         super().__init__(d, bases=bases, products=products)
         if order is None and bases is None:
@@ -608,6 +632,9 @@ class LRBMSReductor(GenericRBSystemReductor):
                 all(len(self.bases[s.id]) >= n for s, n in zip(subs, old.block_dims)):
             prev = old
         planner = _Planner(Handle.get(), owner_rank_of, rank, world, prev=prev)
+        if self.fuse_chains:
+            planner.fuse_cache = self.__dict__.setdefault('_fused_chains', {})
+        planner.narrow_left = self.narrow_left
         if old is not None and getattr(old, 'reusable', False):
             # the reduced model of the previous plan is no longer referenced: recycle its scratch arrays
             pool = {}
