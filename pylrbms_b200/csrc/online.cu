@@ -284,7 +284,7 @@ struct SolveParamsV2 {
   const int32_t* ca_tile;   // operator tile index (into a_tiles) per staged tile
   int32_t n_ca;             // length of ca_tile
   const int4* cdesc;        // per item: {pair begin, late begin, pair end (staged offsets), staged operator tile or -1}
-  const int32_t* cslot;     // per item: window slot (-1: diagonal tile / rhs row)
+  const int32_t* cslot;     // per item: (window slot + 1; 0: diagonal tile / rhs row) | (has a source-(J-2) pair) << 20
   const int32_t* cord;      // per item position: li in hand-out order (longest early update first)
   const int32_t* cnext;     // per item: li of the target in the next column its tile feeds (-1: none)
   const int2* win_ab;       // per pair: window slots of the two operands (a < 0: forward-solve row y_{-a-1})
@@ -294,6 +294,7 @@ struct SolveParamsV2 {
   int32_t max_a_col;
   int32_t back_stage_doubles;
   int32_t plain_deal;       // 1 (LRBMS_SOLVE_BIASED_DEAL=1): warps 4, 8, 12 (the chain warp's scheduler) come last in every round
+  int32_t staggered;        // schedule variant of the symbolic phase (lrbms_symbolic::staggered)
   int32_t no_store;         // timing experiment only (LRBMS_SOLVE_NOSTORE=1): skip the factor store (wrong results)
   long long* timing;        // optional (LRBMS_SOLVE_TIMING=1): [16 warps][8 phases] SM cycles of CTA 0, else NULL
 };
@@ -426,8 +427,10 @@ solve_kernel_v2(SolveParamsV2 P2, int64_t n_mu, const double* __restrict__ theta
     // plain deal is 4.6 % faster per parameter.  LRBMS_SOLVE_BIASED_DEAL=1 brings the old deal back.)
     const int q4 = warp >> 2;
     const bool plain = P2.plain_deal == 0;
-    const int posU = plain ? (warp - 1) : ((warp & 3) ? (warp - 1 - q4) : (10 + q4));
-    const int posR = plain ? (13 - posU) : ((warp & 3) ? (10 - posU) : (14 - q4));
+    // (the triangular solve gives warps 1 .. n_tiles - 14 two tiles and the others one, so the longest early items go to
+    // the *high* warps: warp 14 first)
+    const int posU = plain ? (kUpd - warp) : ((warp & 3) ? (warp - 1 - q4) : (10 + q4));
+    const int posR = plain ? (kUpd - 1 - posU) : ((warp & 3) ? (10 - posU) : (14 - q4));
     for (int r = 0; kUpd * r <= ncol; ++r) {
       const int item = kUpd * r + ((r & 1) ? posR : posU);
       if (item > ncol) continue;
@@ -476,6 +479,13 @@ solve_kernel_v2(SolveParamsV2 P2, int64_t n_mu, const double* __restrict__ theta
     const int mbp = Jy % kMetaBufs;
     const int* slotP = sSlot + mbp * MT;
     const int* nextP = sNext + mbp * MT;
+    // metadata of column Jy + 1: its targets get, besides the late update with the tile formed here, their pair with
+    // source column Jy - 1 (both operands in the window) -- the early updates stop one source column earlier
+    const int mbn = (Jy + 1) % kMetaBufs;
+    const int* slotN = sSlot + mbn * MT;
+    const int4* descN = sDesc + mbn * MT;
+    const int2* pairN = sPair + mbn * P2.max_col_pairs;
+    const int ncolN = (Jy + 1 < P.ntc) ? sCol[Jy + 1].y : 0;
     double2 fbn = make_double2(0.0, 0.0);
     // Slot 0: L_{Jy+1,Jy} (every warp forms it itself instead of waiting for another warp); slots 1, 2: two of this
     // warp's own items.  The three solves are independent, written side by side so their latencies overlap.
@@ -521,7 +531,7 @@ solve_kernel_v2(SolveParamsV2 P2, int64_t n_mu, const double* __restrict__ theta
       for (int k = 1; k < 3; ++k) {
         if (!on[k]) continue;
         if (li[k] < ncol) {
-          *reinterpret_cast<double2*>(win + slotP[li[k]] * 64 + lane * 2) = frag[k];
+          *reinterpret_cast<double2*>(win + ((slotP[li[k]] & 0xfffff) - 1) * 64 + lane * 2) = frag[k];
           if (!P2.no_store) *reinterpret_cast<double2*>(L + (int64_t)(cp0 + li[k]) * 64 + lane * 2) = frag[k];
         } else if (g == 0) {
           sx[8 * Jy + 2 * t] = x0[k];
@@ -531,6 +541,18 @@ solve_kernel_v2(SolveParamsV2 P2, int64_t n_mu, const double* __restrict__ theta
           double n0 = 0.0, n1 = 0.0;
           dmma884(cc[k].x, cc[k].y, -frag[k].x, fbn.x);
           dmma884(n0, n1, -frag[k].y, fbn.y);
+          if (slotN[nl[k]] >> 20) {                       // pair with source column Jy - 1, from the window
+            const int2 ab = pairN[descN[nl[k]].y];
+            double2 fa;
+            if (nl[k] < ncolN) fa = *reinterpret_cast<const double2*>(win + ab.x * 64 + lane * 2);
+            else {                                        // rhs row: the A operand is the forward-solve row y_K
+              const int K = -ab.x - 1;
+              fa = make_double2((g == 0) ? sx[8 * K + t] : 0.0, (g == 0) ? sx[8 * K + 4 + t] : 0.0);
+            }
+            const double2 fb = *reinterpret_cast<const double2*>(win + ab.y * 64 + lane * 2);
+            dmma884(cc[k].x, cc[k].y, -fa.x, fb.x);
+            dmma884(n0, n1, -fa.y, fb.y);
+          }
           *reinterpret_cast<double2*>(accL + nl[k] * 64 + lane * 2) = make_double2(cc[k].x + n0, cc[k].y + n1);
         }
       }
@@ -554,6 +576,18 @@ solve_kernel_v2(SolveParamsV2 P2, int64_t n_mu, const double* __restrict__ theta
       double n0 = 0.0, n1 = 0.0;
       dmma884(cc.x, cc.y, -frag.x, frag.x);
       dmma884(n0, n1, -frag.y, frag.y);
+      *reinterpret_cast<double2*>(accCur + lane * 2) = make_double2(cc.x + n0, cc.y + n1);
+      __syncwarp();
+    }
+    if (sSlot[(Jc % kMetaBufs) * MT] >> 20) {                                              // pair with source column Jc - 2
+      const int2 ab = sPair[(Jc % kMetaBufs) * P2.max_col_pairs + sDesc[(Jc % kMetaBufs) * MT].y];
+      const double2 fa = *reinterpret_cast<const double2*>(win + ab.x * 64 + lane * 2);
+      const double2 fb = *reinterpret_cast<const double2*>(win + ab.y * 64 + lane * 2);
+      double2 cc = *reinterpret_cast<const double2*>(accCur + lane * 2);
+      double n0 = 0.0, n1 = 0.0;
+      dmma884(cc.x, cc.y, -fa.x, fb.x);
+      dmma884(n0, n1, -fa.y, fb.y);
+      __syncwarp();
       *reinterpret_cast<double2*>(accCur + lane * 2) = make_double2(cc.x + n0, cc.y + n1);
       __syncwarp();
     }
@@ -626,12 +660,30 @@ solve_kernel_v2(SolveParamsV2 P2, int64_t n_mu, const double* __restrict__ theta
         diagonal_chain(J, accPrev, accCur, sWprev, sWcur);
         LRBMS_TICK(1);
       } else if (is_upd) {
-        if (J >= 1) solve_column(J - 1, accPrev, accCur, sWprev);
-        LRBMS_TICK(1);
-        asm volatile("bar.sync 1, %0;\n" ::"n"(kUpd * 32) : "memory");   // column J-1 of L visible to the update warps
-        LRBMS_TICK(2);
-        if (J + 1 < P.ntc) early_updates(J + 1, accNext);
-        LRBMS_TICK(3);
+        if (P2.staggered) {
+          // The early updates of column J+1 (source columns <= J-2) do not touch anything the triangular solve of column
+          // J-1 produces, so the two run in either order: odd update warps solve first, even ones second -- the
+          // bandwidth-bound pair loops of one half overlap the latency-bound solves of the other.
+          if (warp & 1) {
+            if (J >= 1) solve_column(J - 1, accPrev, accCur, sWprev);
+            LRBMS_TICK(1);
+            if (J + 1 < P.ntc) early_updates(J + 1, accNext);
+            LRBMS_TICK(3);
+          } else {
+            if (J + 1 < P.ntc) early_updates(J + 1, accNext);
+            LRBMS_TICK(3);
+            if (J >= 1) solve_column(J - 1, accPrev, accCur, sWprev);
+            LRBMS_TICK(1);
+          }
+        } else {
+          // patterns without carrier tiles: early updates include source column J-1, i.e. they follow the solve
+          if (J >= 1) solve_column(J - 1, accPrev, accCur, sWprev);
+          LRBMS_TICK(1);
+          asm volatile("bar.sync 1, %0;\n" ::"n"(kUpd * 32) : "memory");   // column J-1 of L visible to the update warps
+          LRBMS_TICK(2);
+          if (J + 1 < P.ntc) early_updates(J + 1, accNext);
+          LRBMS_TICK(3);
+        }
       }
       cp_async_wait<1>();   // everything staged for column J+2 has landed (column J+3 may still be in flight)
       __syncthreads();
@@ -1085,6 +1137,7 @@ int lrbms_online_plan_create(lrbms_handle_t h, const lrbms_reduced_system_t* sys
       UP_I32(tmp, S.cdesc);  s2.cdesc = reinterpret_cast<const int4*>(tmp);
       UP_I32(tmp, S.win_ab); s2.win_ab = reinterpret_cast<const int2*>(tmp);
       s2.timing = nullptr;
+      s2.staggered = S.staggered;
       { const char* pd = getenv("LRBMS_SOLVE_BIASED_DEAL"); s2.plain_deal = (pd && atoi(pd) > 0) ? 1 : 0; }
       { const char* ns = getenv("LRBMS_SOLVE_NOSTORE"); s2.no_store = (ns && atoi(ns) > 0) ? 1 : 0; }
       if (const char* tenv = getenv("LRBMS_SOLVE_TIMING")) {

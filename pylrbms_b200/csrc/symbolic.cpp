@@ -152,21 +152,53 @@ int lrbms_symbolic_build(lrbms_symbolic& S, int32_t n_sub, const int32_t* sizes,
       }
     }
     S.late_ptr.assign(n_targets, 0);
-    auto set_late = [&](int64_t tgt, int J) {
+    // Pairs of a target in tile column J are sorted by source column.  In the staggered schedule "early" pairs have source
+    // columns <= J - 3: their operands are final two pipeline iterations before the target is, so the pair loop of the early
+    // updates never waits for the triangular solve that runs beside it.  The (at most two) remaining pairs, source columns
+    // J - 2 and J - 1, are applied by the warp that has just formed the tile of column J - 1 in the target's row
+    // (solve_column).  That needs a carrier: tile (I, J - 1) and tile (J, J - 1) must exist for every target (I, J) that has a
+    // source-(J - 2) pair -- always true for a band, not for every sparsity pattern.  Without carriers the schedule falls
+    // back to early = source columns <= J - 2 and the kernel puts a barrier between solve and early updates (staggered = 0).
+    auto sub_exists = [&](int J) {     // tile (J + 1, J)
+      return J >= 0 && J + 1 < S.ntc && S.col_ptr[J + 1] - S.col_ptr[J] >= 2 && S.row_idx[S.col_ptr[J] + 1] == J + 1;
+    };
+    auto tile_exists = [&](int I, int J) {
+      const int32_t* b = S.row_idx.data() + S.col_ptr[J];
+      const int32_t* e = S.row_idx.data() + S.col_ptr[J + 1];
+      const int32_t* it = std::lower_bound(b, e, I);
+      return it != e && *it == I;
+    };
+    auto set_late = [&](int64_t tgt, int J, int back) {
       int32_t lp = S.pair_ptr[tgt + 1];
       if (J >= 1) {
-        const int32_t lim = S.col_ptr[J - 1];
+        const int32_t lim = S.col_ptr[std::max(J - back, 0)];
         lp = S.pair_ptr[tgt];
         while (lp < S.pair_ptr[tgt + 1] && S.pair_b[lp] < lim) ++lp;
       }
       S.late_ptr[tgt] = lp;
     };
+    // the target has a pair with source column J - 2 that is not an early pair (it is the first pair after the early ones)
+    auto has_late2 = [&](int64_t tgt, int J) {
+      const int32_t lp = S.late_ptr[tgt];
+      return J >= 2 && lp < S.pair_ptr[tgt + 1] && S.pair_b[lp] < S.col_ptr[J - 1];
+    };
+    S.staggered = 1;
+    for (int J = 0; J < S.ntc && S.staggered; ++J) {
+      for (int32_t p = S.col_ptr[J]; p <= S.col_ptr[J + 1] && S.staggered; ++p) {
+        const int64_t tgt = (p < S.col_ptr[J + 1]) ? p : n_tiles + J;
+        set_late(tgt, J, 2);
+        if (!has_late2(tgt, J) || tgt == S.col_ptr[J]) continue;          // (the diagonal target needs no carrier)
+        const bool carrier = sub_exists(J - 1) && (tgt >= n_tiles || tile_exists(S.row_idx[tgt], J - 1));
+        if (!carrier) S.staggered = 0;
+      }
+    }
+    const int late_back = S.staggered ? 2 : 1;
     S.xo_ptr.assign(S.ntc + 1, 0);
     S.xo_idx.clear();
     for (int J = 0; J < S.ntc; ++J) {
       std::vector<int32_t> items;
-      for (int32_t p = S.col_ptr[J]; p < S.col_ptr[J + 1]; ++p) { set_late(p, J); items.push_back(p); }
-      set_late(n_tiles + J, J);
+      for (int32_t p = S.col_ptr[J]; p < S.col_ptr[J + 1]; ++p) { set_late(p, J, late_back); items.push_back(p); }
+      set_late(n_tiles + J, J, late_back);
       items.push_back((int32_t)(n_tiles + J));
       std::stable_sort(items.begin(), items.end(), [&](int32_t a, int32_t b) {
         return (S.late_ptr[a] - S.pair_ptr[a]) > (S.late_ptr[b] - S.pair_ptr[b]);
@@ -205,7 +237,8 @@ int lrbms_symbolic_build(lrbms_symbolic& S, int32_t n_sub, const int32_t* sizes,
         d[1] = S.late_ptr[tgt] - shift;
         d[2] = S.pair_ptr[tgt + 1] - shift;
         d[3] = (li < ncol) ? S.a_map[tgt] : -1;
-        S.cslot[xo0 + li] = (li < ncol) ? S.win_slot[tgt] : -1;
+        // window slot + 1 (0: diagonal tile / rhs row) in the low bits, bit 20: the target has a source-(J - 2) pair
+        S.cslot[xo0 + li] = (((li < ncol) ? S.win_slot[tgt] : -1) + 1) | ((S.staggered && has_late2(tgt, J)) ? (1 << 20) : 0);
       }
       // hand-out order of the early updates: longest item first (the kernel deals them to its 15 update warps in
       // snake order: 1..15, 15..1, ...)

@@ -31,13 +31,16 @@ struct lrbms_symbolic {
   // pairs of every target are sorted by source column K; the "late" pairs (K == J - 1, operands produced by the
   // immediately preceding column) start at late_ptr[target]
   std::vector<int32_t> late_ptr;
+  // 1: early pairs stop at source column J - 3 and the source-(J - 2) pair rides with the late update (see symbolic.cpp);
+  // 0: early pairs include source column J - 2 (patterns without a carrier tile for every such pair)
+  int32_t staggered = 1;
   // pair operands as window slots: win_a[p] (or -(K + 1) for the forward-solve row y_K), win_b[p]
   std::vector<int32_t> win_a, win_b;
   // targets of each tile column (tiles of the column, then its rhs target) ordered by decreasing early work
   std::vector<int32_t> xo_ptr, xo_idx;
   // per-column staging tables of the kernel (indexed xo_ptr[J] + li, li = position of the target in its column,
   // the rhs target last):  cdesc = {pair begin, late begin, pair end (all relative to the column's staged pair
-  // list), a_map};  cslot = window slot;  cord = li in hand-out order;  cinfo[J] = {first tile pair, tile pairs,
+  // list), a_map};  cslot = (window slot + 1) | (target has a source-(J - 2) pair) << 20;  cord = li in hand-out order;  cinfo[J] = {first tile pair, tile pairs,
   // first rhs pair, rhs pairs};  win_ab = interleaved (win_a, win_b)
   //   cord = li in hand-out order (longest early update first);  cnext = li of the target (I, J + 1) fed by tile (I, J) (-1: none);
   //   chas[J] = 1 if tile (J + 1, J) exists (then every tile of column J has exactly one "late" consumer in column J + 1)

@@ -146,8 +146,9 @@ def test_symbolic_schedule_replays_to_cholesky(built_library, sx, sy, sizes):
         early = [late_ptr[t_] - pair_ptr[t_] for t_ in items]
         assert early == sorted(early, reverse=True)
         for t_ in items:
-            lim = col_ptr[J - 1] if J >= 1 else 0
+            # early pairs: source columns <= J - 3 (staggered schedule) or <= J - 2 (patterns without carrier tiles)
+            lims = (col_ptr[max(J - 2, 0)], col_ptr[J - 1]) if J >= 1 else (0, 0)
             for p in range(pair_ptr[t_], pair_ptr[t_ + 1]):
-                assert (pair_b[p] >= lim) == (p >= late_ptr[t_]) or J == 0
+                assert J == 0 or any((pair_b[p] >= lim) == (p >= late_ptr[t_]) for lim in lims)
                 assert win_b[p] == win_slot[pair_b[p]]
                 assert win_a[p] == (win_slot[pair_a[p]] if pair_a[p] < n_tiles else -(pair_a[p] - n_tiles + 1))
