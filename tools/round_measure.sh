@@ -13,7 +13,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/${
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $O/${TAG}_ncu_launches.log 2>&1
 # full captures: one run of the projection plan (single stream so that the launches do not overlap) ...
 REPS=1 LRBMS_SINGLE_STREAM=1 ncu --set full --clock-control none --import-source on \
-    -k regex:"project_kernel|spmm_kernel|gram_kernel" -s 80 -c 20 -f -o $O/${TAG}_project python tools/offline_timing.py > $O/${TAG}_ncu_project.log 2>&1
+    -k regex:"project_kernel|spmm_kernel|gram_kernel" -s 72 -c 18 -f -o $O/${TAG}_project python tools/offline_timing.py > $O/${TAG}_ncu_project.log 2>&1
 # ... and the two online kernels
 ncu --set full --clock-control none --import-source on -k regex:"solve_kernel_v2" -s 3 -c 1 -f -o $O/${TAG}_solve \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-offline > $O/${TAG}_ncu_solve.log 2>&1
