@@ -366,6 +366,7 @@ solve_kernel_v2(SolveParamsV2 P2, int64_t n_mu, const double* __restrict__ theta
   int* sNext = sOrd + kMetaBufs * MT;                                             // kMetaBufs * MT
   int* sCaTile = sNext + kMetaBufs * MT;                                          // n_ca
   __shared__ int s_info;
+  __shared__ __align__(8) unsigned long long s_back_bar[kBackStages];            // mbarriers of the backward-substitution ring
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, t = lane & 3;
@@ -704,23 +705,35 @@ solve_kernel_v2(SolveParamsV2 P2, int64_t n_mu, const double* __restrict__ theta
           const int4 col = sCol[Jc];
           double* dst = win + ((P.ntc - 1 - Jc) % kBackStages) * stage;
           const double* src = L + (int64_t)col.x * 64;
-          // warp 0 runs the serial chain and issues no copies
-          const int tid = (int)threadIdx.x - 32;
-          if (tid >= 0) {
-            for (int c = tid; c < col.y * 32; c += kV2Threads - 32) cp_async16(dst + 2 * c, src + 2 * c);
-            int* rdst = sSlot + ((P.ntc - 1 - Jc) % kBackStages) * MT;   // sSlot/sOrd/sNext are free now: 15 MT ints
-            if (tid < col.y) cp_async4(rdst + tid, P.row_idx + col.x + tid);
+          // one bulk copy (TMA engine) per tile column, completing on the stage's mbarrier; the n-th use of a stage waits
+          // for parity n & 1.  (768 cp.async per column kept fifteen warps ~450 cycles per column in the copy queue.)
+          const int sidx = (P.ntc - 1 - Jc) % kBackStages;
+          if (threadIdx.x == 32) {
+            mbar_expect_tx(&s_back_bar[sidx], (unsigned)(col.y * 512));
+            bulk_copy_g2s(dst, src, (unsigned)(col.y * 512), &s_back_bar[sidx]);
           }
+          const int tid = (int)threadIdx.x - 64;
+          int* rdst = sSlot + sidx * MT;                               // sSlot/sOrd/sNext are free now: 15 MT ints
+          if (tid >= 0 && tid < col.y) cp_async4(rdst + tid, P.row_idx + col.x + tid);
         }
         cp_async_commit();
       };
+      auto wait_column = [&](int Jc) {
+        if (Jc >= 0) mbar_wait(&s_back_bar[(P.ntc - 1 - Jc) % kBackStages], (unsigned)(((P.ntc - 1 - Jc) / kBackStages) & 1));
+      };
+      __syncthreads();                                  // everybody is through with the window
+      if (threadIdx.x == 0)
+        for (int i = 0; i < kBackStages; ++i) mbar_init(&s_back_bar[i], 1);
+      fence_proxy_async();                              // ... which the bulk copies overwrite
       for (int i = threadIdx.x; i < 2 * kV2Warps * 8; i += kV2Threads) sred[i] = 0.0;
+      __syncthreads();
       for (int s = 0; s < kBackStages - 2; ++s) issue(P.ntc - 1 - s);
       cp_async_wait<kBackStages - 4>();       // columns ntc-1 and ntc-2 have landed
       __syncthreads();
       for (int J = P.ntc - 1; J >= 0; --J) {
         issue(J - (kBackStages - 2));
         if (warp == 0) {
+          wait_column(J);
           const int bsel = (P.ntc - 1 - J) % kBackStages;
           const double* buf = win + bsel * stage;
           const double* red = sred + (J & 1) * kV2Warps * 8;
@@ -752,6 +765,7 @@ solve_kernel_v2(SolveParamsV2 P2, int64_t n_mu, const double* __restrict__ theta
         } else {
           double s0 = 0.0, s1 = 0.0;           // partial sums of column J-1 for solution components t and t + 4
           if (J >= 1) {
+            wait_column(J - 1);
             const int bsel = (P.ntc - J) % kBackStages;
             const double* buf = win + bsel * stage;
             const int* rows = sSlot + bsel * MT;
