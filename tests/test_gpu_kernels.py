@@ -425,6 +425,30 @@ def test_online_solve_matches_dense(handle, sx, sy, sizes, force_v1, monkeypatch
         assert np.linalg.norm(A @ u[m] - f) <= RTOL * np.linalg.norm(f) * np.linalg.cond(A) ** 0.5
 
 
+def test_online_solve_is_bit_reproducible(handle, monkeypatch):
+    """The column pipeline of solve_kernel_v2 lets the two halves of its update warps run the triangular solve and the pair
+    loop in opposite order with a single barrier per tile column; a data race there would show as run-to-run differences.
+    Same parameters in a different order and batch size must give bit-identical solutions."""
+    monkeypatch.delenv('LRBMS_SOLVE_V1', raising=False)
+    rng = np.random.default_rng(77)
+    sysd = _random_reduced_system(rng, 8, 8, [20] * 64)              # C2 reduced-system shape
+    plan, _ = _make_online_plan(handle, sysd)
+    n_mu = 900                                                       # six parameters per resident CTA
+    theta = np.column_stack([np.ones(n_mu), rng.uniform(0.1, 1.0, n_mu), rng.uniform(0.5, 2.0, n_mu)])
+    u1, info1 = _run_sweep(handle, plan, sysd, theta, with_est=False)
+    u2, info2 = _run_sweep(handle, plan, sysd, theta, with_est=False)
+    assert np.all(info1 == 0) and np.array_equal(u1, u2)
+    perm = rng.permutation(n_mu)[:333]
+    u3, _ = _run_sweep(handle, plan, sysd, theta[perm], with_est=False)
+    assert np.array_equal(u3, u1[perm])
+    # every parameter against the dense solve, not a sample
+    for m in range(n_mu):
+        A = theta[m, 0] * sysd['dense'][0] + theta[m, 1] * sysd['dense'][1]
+        ref = np.linalg.solve(A, theta[m, 2] * sysd['rhs'][0])
+        e = u1[m] - ref
+        assert np.sqrt(e @ A @ e) <= RTOL * np.sqrt(ref @ A @ ref), 'mu {}'.format(m)
+
+
 def test_online_solve_flags_indefinite_system(handle):
     rng = np.random.default_rng(5)
     sysd = _random_reduced_system(rng, 2, 2, [6, 6, 6, 6])
