@@ -40,8 +40,8 @@ UNIT = 'solves+estimates/s'
 # DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed `ncu --set full` captures
 # of the default workload (profiles/r01c_ncu_full_*_raw.csv); null for any other workload.
 NCU_TRAFFIC_BYTES = {
-    'solve_kernel_v2': 13.035e9 + 16.439e9,           # 10 000 parameters per launch
-    'projection_plan': 3.994e9 + 0.823e9,             # SpMM stages >= 1 + the plan: 6 spmm + 4 project + 5 gram launches
+    'solve_kernel_v2': 13.123e9 + 16.438e9,           # 10 000 parameters per launch
+    'projection_plan': 3.995e9 + 0.826e9,             # SpMM stages >= 1 + the plan: 6 spmm + 4 project + 5 gram launches
 }
 
 
