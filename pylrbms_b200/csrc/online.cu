@@ -806,7 +806,7 @@ solve_kernel_v2(SolveParamsV2 P2, int64_t n_mu, const double* __restrict__ theta
 constexpr int kEstThreads = 512;
 constexpr int kEstWarps = kEstThreads / 32;
 // parameters per CTA (template argument kTMU: 64, 32, 16 or 8): every estimator matrix is read once per kTMU parameters.
-// 64 unless the neighbourhood vectors of that many parameters do not fit the shared memory (3D neighbourhoods, N = 40).
+// 32 when two CTAs of that size fit one SM, else the largest that fits (3D neighbourhoods with N = 40: 16).
 // shared row stride kTMU + 4 (doubles): 4 or 12 mod 16 -> conflict-free DMMA fragment loads
 constexpr int kTMUMax = 64;
 constexpr int kMaxEstTerms = 64; // terms per subdomain
@@ -829,7 +829,7 @@ struct EstParams {
 };
 
 template <int kTMU>
-__global__ void __launch_bounds__(kEstThreads, 1)
+__global__ void __launch_bounds__(kEstThreads, (kTMU <= 32) ? 2 : 1)
 estimate_kernel(EstParams P, int64_t n_mu, const double* __restrict__ theta, const double* __restrict__ u,
                 double* __restrict__ parts) {
   constexpr int kLDX = kTMU + 4;
@@ -1234,7 +1234,10 @@ int lrbms_online_plan_create(lrbms_handle_t h, const lrbms_reduced_system_t* sys
     auto est_bytes = [&](int tmu) {
       return sizeof(double) * ((size_t)(ep.dmax_pad + ep.qdmax_pad) * (tmu + 4) + (size_t)Q * tmu + kEstWarps * 3 * tmu);
     };
-    P->est_tmu = kTMUMax;
+    // 32 parameters per CTA when two such CTAs fit one SM (the staging phase of one overlaps the DMMAs of the other:
+    // 4.5 instead of 5.4 ms per 10 000 parameters at C2), else the largest tile that fits at all
+    P->est_tmu = (2 * (est_bytes(32) + 1024) <= (size_t)h->max_smem_optin) ? 32 : kTMUMax;
+    if (const char* e = getenv("LRBMS_EST_TMU")) { const int v = atoi(e); if (v == 8 || v == 16 || v == 32 || v == 64) P->est_tmu = v; }
     while (P->est_tmu > 8 && est_bytes(P->est_tmu) > (size_t)h->max_smem_optin) P->est_tmu /= 2;
     P->est_smem = est_bytes(P->est_tmu);
     if (P->est_smem > (size_t)h->max_smem_optin) {
