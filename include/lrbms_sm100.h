@@ -167,7 +167,9 @@ int lrbms_symbolic_create(int32_t n_sub, const int32_t* basis_sizes, int32_t n_b
                           const int32_t* block_j, lrbms_symbolic_t* out);
 int lrbms_symbolic_destroy(lrbms_symbolic_t s);
 /* what: 0 n_red, 1 padded n, 2 tile columns, 3 L tiles, 4 A tiles, 5 update pairs, 6 factor flops per mu,
- *       7 max targets per tile column, 8 shared-memory window slots (live off-diagonal L tiles, peak) */
+ *       7 max targets per tile column, 8 shared-memory window slots (live off-diagonal L tiles, peak),
+ *       11 schedule variant of the shared-memory kernel: 1 = early updates stop at source column J - 3 and the pair with
+ *          source column J - 2 rides with the late update (every such pair has a carrier tile), 0 = barrier schedule */
 int lrbms_symbolic_info(lrbms_symbolic_t s, int32_t what, int64_t* out);
 /* copy out schedule arrays (for tests): which: 0 col_ptr[ntc+1], 1 row_idx[n_tiles], 2 pair_ptr[n_tiles+ntc+1],
  * 3 pair_a, 4 pair_b, 5 a_map[n_tiles], 6 win_slot[n_tiles], 7 late_ptr[n_tiles+ntc], 8 win_a[pairs], 9 win_b[pairs],

@@ -267,6 +267,7 @@ class Symbolic:
     flops = property(lambda self: self.info(6))
     max_targets = property(lambda self: self.info(7))
     n_win_slots = property(lambda self: self.info(8))
+    staggered = property(lambda self: self.info(11))
 
     def get(self, which):
         sizes = {0: self.n_tile_cols + 1, 1: self.n_tiles, 2: self.n_tiles + self.n_tile_cols + 1, 3: self.n_pairs,

@@ -327,6 +327,7 @@ int lrbms_symbolic_info(lrbms_symbolic_t s, int32_t what, int64_t* out) {
     case 8: *out = s->n_win_slots; break;
     case 9: *out = s->max_col_pairs; break;
     case 10: *out = s->max_a_col; break;
+    case 11: *out = s->staggered; break;
     default: return LRBMS_ERR_INVALID;
   }
   return LRBMS_OK;

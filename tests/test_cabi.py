@@ -152,3 +152,27 @@ def test_symbolic_schedule_replays_to_cholesky(built_library, sx, sy, sizes):
                 assert J == 0 or any((pair_b[p] >= lim) == (p >= late_ptr[t_]) for lim in lims)
                 assert win_b[p] == win_slot[pair_b[p]]
                 assert win_a[p] == (win_slot[pair_a[p]] if pair_a[p] < n_tiles else -(pair_a[p] - n_tiles + 1))
+
+
+def test_symbolic_schedule_variant(built_library):
+    """Band patterns (2D grids of subdomains) get the staggered schedule of solve_kernel_v2; a pattern in which a target has
+    a source-(J-2) pair but no carrier tile falls back to the barrier schedule.  Either way the pair lists are complete
+    (the replay test above) and late_ptr splits them at the right source column."""
+    from pylrbms_b200._lib import Symbolic
+    blocks = _grid_blocks(8, 8)
+    sym = Symbolic(np.full(64, 20, dtype=np.int32), [b[0] for b in blocks], [b[1] for b in blocks])
+    assert sym.staggered == 1
+    # subdomains 2 and 3 (one 8x8 tile each) couple to 0, which fills tile (3, 2) from source column 0 = J - 2; subdomain 1 is
+    # isolated, so neither tile (3, 1) nor (2, 1) exists to carry that pair
+    S = 4
+    blocks = [(i, i) for i in range(S)] + [(2, 0), (0, 2), (3, 0), (0, 3)]
+    sym2 = Symbolic(np.full(S, 8, dtype=np.int32), [b[0] for b in blocks], [b[1] for b in blocks])
+    assert sym2.staggered == 0
+    col_ptr, row_idx, pair_ptr, pair_a, pair_b = (sym2.get(k) for k in range(5))
+    late_ptr = sym2.get(7)
+    back = 2 if sym2.staggered else 1
+    for J in range(sym2.n_tile_cols):
+        for tgt in list(range(col_ptr[J], col_ptr[J + 1])) + [sym2.n_tiles + J]:
+            lim = col_ptr[max(J - back, 0)] if J >= 1 else 0
+            for p in range(pair_ptr[tgt], pair_ptr[tgt + 1]):
+                assert J == 0 or (pair_b[p] >= lim) == (p >= late_ptr[tgt])

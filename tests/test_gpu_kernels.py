@@ -284,8 +284,9 @@ def test_project_all_zero_operator(handle):
 #  online: solve / estimate against dense NumPy
 # ------------------------------------------------------------------------------------------------------------
 
-def _random_reduced_system(rng, sx, sy, sizes, Q=2, Qf=1):
-    """Random SPD block-sparse affine system on an sx x sy subdomain grid + random estimator terms."""
+def _random_reduced_system(rng, sx, sy, sizes, Q=2, Qf=1, couplings=None):
+    """Random SPD block-sparse affine system on an sx x sy subdomain grid (or with the given symmetric list of coupled
+    subdomain pairs) + random estimator terms."""
     S = sx * sy
     sizes = np.asarray(sizes, dtype=np.int32)
     assert len(sizes) == S
@@ -295,12 +296,15 @@ def _random_reduced_system(rng, sx, sy, sizes, Q=2, Qf=1):
     for s in range(S):
         ix, iy = s % sx, s // sx
         nb = [s]
-        if iy > 0: nb.append(s - sx)
-        if ix > 0: nb.append(s - 1)
-        if ix < sx - 1: nb.append(s + 1)
-        if iy < sy - 1: nb.append(s + sx)
-        nbh.append(sorted(nb))
-        for j in sorted(nb):
+        if couplings is not None:
+            nb += [j for (i, j) in couplings if i == s] + [i for (i, j) in couplings if j == s]
+        else:
+            if iy > 0: nb.append(s - sx)
+            if ix > 0: nb.append(s - 1)
+            if ix < sx - 1: nb.append(s + 1)
+            if iy < sy - 1: nb.append(s + sx)
+        nbh.append(sorted(set(nb)))
+        for j in sorted(set(nb)):
             blocks.append((s, j))
     dense = []
     for q in range(Q):
@@ -446,6 +450,30 @@ def test_online_solve_is_bit_reproducible(handle, monkeypatch):
         A = theta[m, 0] * sysd['dense'][0] + theta[m, 1] * sysd['dense'][1]
         ref = np.linalg.solve(A, theta[m, 2] * sysd['rhs'][0])
         e = u1[m] - ref
+        assert np.sqrt(e @ A @ e) <= RTOL * np.sqrt(ref @ A @ ref), 'mu {}'.format(m)
+
+
+def test_online_solve_barrier_schedule(handle, monkeypatch):
+    """A sparsity pattern in which a target has a pair with source column J - 2 but no carrier tile in column J - 1: the
+    symbolic phase must pick the barrier schedule of solve_kernel_v2 and the kernel must still reproduce the dense solve."""
+    from pylrbms_b200._lib import Symbolic
+    monkeypatch.delenv('LRBMS_SOLVE_V1', raising=False)
+    rng = np.random.default_rng(21)
+    # subdomains 2 and 3 couple to 0 (fill in (3, 2) from source 0); subdomain 1 is isolated: no tile (3, 1) or (2, 1)
+    couplings = [(2, 0), (3, 0), (5, 4), (6, 4), (6, 2)]
+    sizes = [8, 8, 8, 8, 16, 8, 11]
+    sysd = _random_reduced_system(rng, len(sizes), 1, sizes, couplings=couplings)
+    sym = Symbolic(sysd['sizes'], [b[0] for b in sysd['blocks']], [b[1] for b in sysd['blocks']])
+    assert sym.staggered == 0
+    plan, _ = _make_online_plan(handle, sysd)
+    n_mu = 41
+    theta = np.column_stack([np.ones(n_mu), rng.uniform(0.1, 1.0, n_mu), rng.uniform(0.5, 2.0, n_mu)])
+    u, info = _run_sweep(handle, plan, sysd, theta, with_est=False)
+    assert np.all(info == 0)
+    for m in range(n_mu):
+        A = theta[m, 0] * sysd['dense'][0] + theta[m, 1] * sysd['dense'][1]
+        ref = np.linalg.solve(A, theta[m, 2] * sysd['rhs'][0])
+        e = u[m] - ref
         assert np.sqrt(e @ A @ e) <= RTOL * np.sqrt(ref @ A @ ref), 'mu {}'.format(m)
 
 
