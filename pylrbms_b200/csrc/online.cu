@@ -332,15 +332,6 @@ __device__ __forceinline__ void apply_pairs(const int2* __restrict__ pairs, cons
   }
 }
 
-// accumulator layout (T[g][2t], T[g][2t+1]) -> operand-fragment layout (T[g][t], T[g][t+4])
-__device__ __forceinline__ double2 acc_to_frag(int lane, double x0, double x1) {
-  const int t = lane & 3;
-  const int s1 = (lane & ~3) | (t >> 1), s2 = s1 | 2;
-  const double e0 = __shfl_sync(0xffffffffu, x0, s1), e1 = __shfl_sync(0xffffffffu, x1, s1);
-  const double f0 = __shfl_sync(0xffffffffu, x0, s2), f1 = __shfl_sync(0xffffffffu, x1, s2);
-  return make_double2((t & 1) ? e1 : e0, (t & 1) ? f1 : f0);
-}
-
 __global__ void __launch_bounds__(kV2Threads, 1)
 solve_kernel_v2(SolveParamsV2 P2, int64_t n_mu, const double* __restrict__ theta, double* __restrict__ u,
                 int32_t* __restrict__ info, double* __restrict__ work) {
