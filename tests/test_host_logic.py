@@ -87,3 +87,49 @@ def test_bench_flop_model_matches_survey():
     fl = bench.survey_flops_per_mu(8, 20, 2)
     assert fl['n_red'] == 1280 and fl['blocks'] == 288 and fl['half_bandwidth'] == 180
     assert abs(fl['solve'] - (0.46e6 + 41.5e6 + 0.92e6)) < 0.1e6
+
+
+def test_synthetic_3d_fixture_structure():
+    """The seeded synthetic operator set with 3D structure (config C4 shape): symmetry and definiteness where the hot path
+    relies on them, interface-only coupling blocks, six-neighbour subdomain graph, determinism by seed."""
+    import scipy.sparse as sp
+    from pylrbms_b200.synthetic_fixture import make_random_local_bases, synthetic_block_operators
+    data = synthetic_block_operators((3, 2, 2), (2, 2, 2), seed=5)
+    again = synthetic_block_operators((3, 2, 2), (2, 2, 2), seed=5)
+    other = synthetic_block_operators((3, 2, 2), (2, 2, 2), seed=6)
+    S = data.num_subdomains
+    assert S == 12 and data.Q == 2 and max(len(nb) for nb in data.neighborhoods) == 5      # 3x2x2: at most 4 face neighbours
+    assert synthetic_block_operators((3, 3, 3), (1, 1, 1), seed=1).neighborhoods[13] == [4, 10, 12, 13, 14, 16, 22]
+    for q in range(2):
+        for key, M in data.lhs[q].items():
+            assert (abs(M - again.lhs[q][key])).nnz == 0
+            i, j = key
+            assert abs(M - data.lhs[q][(j, i)].T).max() == 0.0                               # A_q[j, i] = A_q[i, j]^T
+    assert abs(data.lhs[0][(0, 0)] - other.lhs[0][(0, 0)]).max() > 0
+    # coupling blocks: non-zero rows only (interface cells), fewer than the diagonal block has
+    for (i, j), M in data.lhs[0].items():
+        if i != j:
+            rows = np.unique(M.nonzero()[0])
+            assert 0 < len(rows) < M.shape[0]
+    # A(mu) = A_0 + mu A_1 is SPD over the parameter range
+    n = int(data.n.sum())
+    off = np.concatenate([[0], np.cumsum(data.n)])
+    for mu in data.parameter_range:
+        A = np.zeros((n, n))
+        for (i, j) in data.lhs[0]:
+            A[off[i]:off[i + 1], off[j]:off[j + 1]] = (data.lhs[0][(i, j)] + mu * data.lhs[1][(i, j)]).toarray()
+        assert np.abs(A - A.T).max() == 0.0 and np.linalg.eigvalsh(A).min() > 0.0
+    for i in range(S):
+        for M in (data.l2[i], data.energy[i], data.elliptic[i]):
+            assert abs(M - M.T).max() <= 1e-15 and np.linalg.eigvalsh(M.toarray()).min() > 0.0
+        assert abs(data.bb[i] - data.bb[i].T).max() == 0.0
+        assert abs(data.aa[0][1][i] - data.aa[1][0][i].T).max() == 0.0
+        assert data.div[i].shape == (data.n[i], data.m[i]) and data.ab[1][i].shape == (data.n[i], data.m[i])
+        for k in data.neighborhoods[i]:
+            assert data.oi[(i, k)].shape == (data.n[k], data.n[i])
+            assert data.fr[1][(i, k)].shape == (data.m[k], data.n[i])
+    # bases: orthonormal in the local energy product, shape functions first
+    bases = make_random_local_bases(data, [3 + (i % 4) for i in range(S)], seed=2)
+    for i, V in enumerate(bases):
+        G = V @ (data.energy[i] @ V.T)
+        assert np.abs(G - np.eye(len(V))).max() < 1e-10
