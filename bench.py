@@ -37,12 +37,25 @@ sys.path.insert(0, ROOT)
 METRIC = 'online reduced solves+estimates/s (mu-batched)'
 UNIT = 'solves+estimates/s'
 
-# DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed `ncu --set full` captures
-# of the default workload (profiles/r01c_ncu_full_*_raw.csv); null for any other workload.
-NCU_TRAFFIC_BYTES = {
-    'solve_kernel_v2': 13.123e9 + 16.438e9,           # 10 000 parameters per launch
-    'projection_plan': 3.995e9 + 0.826e9,             # SpMM stages >= 1 + the plan: 6 spmm + 4 project + 5 gram launches
-}
+
+
+def ncu_traffic(kernel, workload):
+    """DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed ``ncu --set full`` capture
+    of this round (``profiles/traffic.json``, written by ``tools/ncu_summary.py`` from the raw pages).  An entry only counts
+    if it was captured from the *same kernel source* (sha256 of the .cu file, recorded next to the numbers) and the same
+    workload string -- after a kernel change the figure goes to null instead of silently going stale."""
+    import hashlib
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as f:
+            table = json.load(f)
+        e = table[kernel]
+        with open(os.path.join(ROOT, 'pylrbms_b200', 'csrc', e['source']), 'rb') as f:
+            sha = hashlib.sha256(f.read()).hexdigest()
+        if sha != e['source_sha256'] or e['workload'] != workload:
+            return None
+        return float(e['dram_bytes_per_launch'])
+    except Exception:
+        return None
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -62,18 +75,43 @@ def parse_args():
     ap.add_argument('--cpu-sample', type=int, default=24, help='parameters per CPU-baseline step')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-offline', action='store_true')
+    ap.add_argument('--offline-only', action='store_true', help='stop after the offline half (and its sharded run at N > 1)')
+    ap.add_argument('--no-parity', action='store_true', help='skip the oracle parity gate (it runs whenever the oracle fits)')
+    ap.add_argument('--eta-only', action='store_true', help='e2e ships eta only (ReducedModel.sweep_eta_into), not the solutions')
+    ap.add_argument('--no-c5', dest='c5', action='store_false', help='skip the 125 000-parameter-per-GPU sweep (configs[4])')
+    ap.add_argument('--no-c3-sharded', dest='c3_sharded', action='store_false',
+                    help='at N > 1: skip the subdomain-sharded offline projection of configs[2] (SPE10-like, 16x16 subdomains)')
+    ap.add_argument('--problem', default='os2015', choices=['os2015', 'spe10'],
+                    help="spe10: the high-contrast (1e6) SPE10-like field of configs[2]")
+    ap.add_argument('--config', default=None, choices=['c2', 'c3', 'c4', 'c5'],
+                    help='shorthand for a BASELINE.json configuration: c2 = the default; c3 = --problem spe10 --subdomains 16 '
+                         '--n-mu 2048; c4 = --synthetic3d 4,4,4 --subdomains 8 --basis 40 --n-mu 64 (full-size reduced system, '
+                         'small fine grid); c5 = --n-mu 125000 --eta-only')
     ap.add_argument('--seed', type=int, default=1002)
     ap.add_argument('--synthetic3d', default=None, metavar='HX,HY,HZ',
                     help='seeded synthetic operators with 3D structure (config C4 shape): --subdomains per direction, '
                          'HX x HY x HZ cells of 4 dofs per subdomain (16,16,12 -> n_i = 12288); offline measurements only')
-    return ap.parse_args()
+    a = ap.parse_args()
+    if a.config == 'c3':
+        a.problem, a.subdomains, a.n_mu, a.c5 = 'spe10', 16, 2048, False
+    elif a.config == 'c4':
+        a.synthetic3d, a.subdomains, a.basis, a.n_mu, a.c5 = '4,4,4', 8, 40, 64, False
+    elif a.config == 'c5':
+        a.n_mu, a.eta_only, a.c5 = 125000, True, False
+    return a
+
+
+def problem_name(a):
+    return 'OS2015' if a.problem == 'os2015' else 'SPE10-like (contrast 1e6)'
 
 
 def workload_name(a):
     if a.synthetic3d:
         h = [int(x) for x in a.synthetic3d.split(',')]
-        return 'synthetic 3D {0}x{0}x{0} subdomains, n_i={1}, N={2}, Q=2'.format(a.subdomains, 4 * h[0] * h[1] * h[2], a.basis)
-    return 'OS2015 {0}x{0} subdomains, n_i={1}, N={2}, Q=2, {3} mu per GPU'.format(a.subdomains, 6 * a.cells ** 2, a.basis, a.n_mu)
+        return 'synthetic 3D {0}x{0}x{0} subdomains, n_i={1}, N={2}, Q=2, {3} mu per GPU'.format(
+            a.subdomains, 4 * h[0] * h[1] * h[2], a.basis, a.n_mu)
+    return '{0} {1}x{1} subdomains, n_i={2}, N={3}, Q=2, {4} mu per GPU'.format(problem_name(a), a.subdomains, 6 * a.cells ** 2,
+                                                                               a.basis, a.n_mu)
 
 
 def make_inputs(a):
@@ -84,30 +122,38 @@ def make_inputs(a):
         data = synthetic_block_operators((a.subdomains,) * 3, h, seed=a.seed)
         bases = make_random_local_bases(data, a.basis, seed=a.seed)
         return data, {'domain_%d' % i: bases[i] for i in range(data.num_subdomains)}
-    data = assemble_block_swipdg((a.subdomains, a.subdomains), a.cells)
+    problem = None
+    if a.problem == 'spe10':
+        from pylrbms_b200.swipdg_fixture import spe10_like_problem
+        problem = spe10_like_problem(seed=1003, contrast=1e6)
+    data = assemble_block_swipdg((a.subdomains, a.subdomains), a.cells, problem=problem)
     bases = make_local_bases(data, a.basis, seed=a.seed)
     return data, {'domain_%d' % i: bases[i] for i in range(data.num_subdomains)}
 
 
-def make_mus(a, rank, n):
+def make_mus(a, rank, n, data=None):
     rng = np.random.default_rng(a.seed + 7919 * rank)
-    return rng.uniform(0.1, 1.0, n)
+    lo, hi = tuple(data.parameter_range) if data is not None else (0.1, 1.0)
+    return rng.uniform(lo, hi, n)
 
 
-def survey_flops_per_mu(sx, N, Q):
+def survey_flops_per_mu(a, data, rd):
+    return survey_flops_model(rd.block_dims, data.neighborhoods, data.Q, rd.half_bandwidth)
+
+
+def survey_flops_model(N, nbh, Q, half_bandwidth):
     """Algorithmic flops of one solve+estimate, SURVEY.md section 8d: assemble 2 Q B N^2, banded Cholesky n b^2,
-    two triangular solves 4 n b, estimator sum_i 2 (d_i^2 + 2 (Q d_i)^2 + Q^2 N^2 + Q^2 N d_i + Q d_i)."""
-    S = sx * sx
-    n = S * N
-    B = S + 2 * 2 * sx * (sx - 1)                 # diagonal + directed face-neighbour blocks
-    b = (sx + 1) * N                              # scalar half bandwidth, lexicographic ordering
+    two triangular solves 4 n b, estimator sum_i 2 (d_i^2 + 2 (Q d_i)^2 + Q^2 N^2 + Q^2 N d_i + Q d_i), with b the scalar half
+    bandwidth of the lexicographically ordered reduced operator (2D: (sx + 1) N; 3D: (sx sy + 1) N) and d_i the summed basis
+    sizes over the neighbourhood of subdomain i."""
+    n = int(sum(N))
+    B = sum(len(x) for x in nbh)                  # diagonal + directed face-neighbour blocks
+    b = half_bandwidth + 1
     est = 0
-    for s in range(S):
-        ix, iy = s % sx, s // sx
-        nb = 1 + (ix > 0) + (ix < sx - 1) + (iy > 0) + (iy < sx - 1)
-        d = nb * N
-        est += 2 * (d * d + 2 * (Q * d) ** 2 + Q * Q * N * N + Q * Q * N * d + Q * d)
-    solve = 2 * Q * B * N * N + n * b * b + 4 * n * b
+    for s_, nb in enumerate(nbh):
+        d = sum(N[k] for k in nb)
+        est += 2 * (d * d + 2 * (Q * d) ** 2 + Q * Q * N[s_] ** 2 + Q * Q * N[s_] * d + Q * d)
+    solve = 2 * Q * sum(N[i] * N[j] for i, nb in enumerate(nbh) for j in nb) + n * b * b + 4 * n * b
     return dict(solve=float(solve), estimate=float(est), total=float(solve + est), n_red=n, blocks=B, half_bandwidth=b)
 
 
@@ -330,6 +376,174 @@ def measured_peaks():
         return 6650.0, 'fallback 6.65 TB/s (B200_PROFILING.md)'
 
 
+def offline_workload_name(a):
+    if a.synthetic3d:
+        return workload_name(a)
+    return '{0} {1}x{1} subdomains, n_i={2}, N={3}, Q=2 (offline)'.format(problem_name(a), a.subdomains, 6 * a.cells ** 2, a.basis)
+
+
+def measure_offline(a, torch, planner, d, bases, fp64_peak, flush_l2, t_reduce_first, reductor):
+    """Kernel-only timing of the batched projection (inputs resident in HBM) + the wall time of reductor.reduce()."""
+    from pylrbms_b200 import LRBMSReductor
+    st = planner.stats()
+    for _ in range(max(3, a.warmup)):
+        planner.run()
+    times_all, times_proj = [], []
+    for _ in range(max(3, a.steps)):
+        flush_l2()
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        e0.record()
+        planner.spmm_plans[0].run()        # stage 0: Oswald / flux-reconstruction images of the bases (rows a2, a3)
+        e1.record()
+        for p in planner.spmm_plans[1:]:   # later stages belong to the projection: D R, and A^T L of the narrow-left chains
+            p.run()
+        planner.project_plan.run()
+        e2.record()
+        e2.synchronize()
+        times_all.append(e0.elapsed_time(e2)); times_proj.append(e1.elapsed_time(e2))
+    hbm_peak, hbm_src = measured_peaks()
+    pp = planner.project_plan
+    t_proj = float(np.mean(times_proj)) * 1e-3
+    # EXECUTED work of the plan that was timed: the later SpMM stages + the projection plan (tight byte count: every array
+    # once).  This is what `frac` is computed from.  The SURVEY section 8d formulation (every operator chain applied matrix by
+    # matrix to the right-hand array, as the reference defines the operators) asks for more flops than the restructured plan
+    # executes; it is reported as an aside (`*_survey_formulation`), not as the roofline fraction.
+    ex_flops = pp.flops + sum(p.flops for p in planner.spmm_plans[1:])
+    ex_bytes = pp.algorithmic_bytes + sum(p.algorithmic_bytes for p in planner.spmm_plans[1:])
+    acct = LRBMSReductor(d, bases=bases)
+    acct.fuse_chains, acct.narrow_left = False, False
+    acct_plan = acct.build_plan()
+    sv_bytes = acct_plan.project_plan.algorithmic_bytes_survey
+    sv_flops = acct_plan.project_plan.flops
+    del acct, acct_plan
+    tfs, gbs = ex_flops / t_proj / 1e12, ex_bytes / t_proj / 1e9
+    ai = ex_flops / ex_bytes
+    crossover = fp64_peak * 1e12 / (hbm_peak * 1e9)
+    tensor_bound = ai > crossover
+    roof = {'bound': 'tensor' if tensor_bound else 'hbm',
+            'kernel': 'projection plan (all buckets of one run: spmm_kernel, project_kernel, gram_kernel)',
+            'achieved': tfs if tensor_bound else gbs, 'peak': fp64_peak if tensor_bound else hbm_peak,
+            'unit': 'TFLOP/s' if tensor_bound else 'GB/s',
+            'frac': tfs / fp64_peak if tensor_bound else gbs / hbm_peak,
+            'traffic': ncu_traffic('projection_plan', offline_workload_name(a)),
+            'peak_source': 'cuBLAS DGEMM 4096^3 measured in this run (FP64 tensor pipe)' if tensor_bound else hbm_src,
+            'counts': 'executed by the timed plan', 'flops': ex_flops, 'bytes': ex_bytes,
+            'arithmetic_intensity_flop_per_byte': ai, 'crossover_flop_per_byte': crossover,
+            'fp64_tflops': tfs, 'fp64_peak_tflops': fp64_peak, 'fp64_frac': tfs / fp64_peak,
+            'hbm_gbs': gbs, 'hbm_peak_gbs': hbm_peak, 'hbm_frac': gbs / hbm_peak, 'hbm_peak_source': hbm_src,
+            'survey_formulation': {'flops': sv_flops, 'bytes': sv_bytes, 'fp64_frac': sv_flops / t_proj / 1e12 / fp64_peak,
+                                   'hbm_frac': sv_bytes / t_proj / 1e9 / hbm_peak,
+                                   'note': 'SURVEY 8d work count of the operators as the reference defines them; the plan '
+                                           'executes less (fused chains, narrow-left), so this is not a kernel efficiency'}}
+    # end to end through the public API: reductor.reduce() from the bases to a reduced model whose blocks are readable
+    reductor.reuse_plan = False
+    t_e2e = []
+    for _ in range(3):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        rd_ = reductor.reduce()
+        rd_.operator.operators[0].sblocks[0]            # reduced blocks live in rd_'s buffer
+        torch.cuda.synchronize()
+        t_e2e.append(time.perf_counter() - t0)
+    return {
+        'metric': 'offline projection HBM GB/s', 'unit': 'GB/s', 'value': sv_bytes / t_proj / 1e9,
+        'value_note': 'BASELINE metric: SURVEY 8d algorithmic bytes / projection time; roofline.frac uses executed counts',
+        'workload': offline_workload_name(a),
+        'ms_all_stages': float(np.mean(times_all)), 'ms_projection': float(np.mean(times_proj)),
+        'ms_projection_covers': 'SpMM stages >= 1 (divergence images, A^T L of narrow-left chains) + the projection plan; '
+                                'stage 0 (Oswald / flux-reconstruction images of the bases) is the rest of ms_all_stages',
+        'projection_descriptors': planner.n_project_descs, 'spmm_descriptors': planner.n_spmm_descs,
+        'launches_per_reduce': st['launches'], 'roofline': roof,
+        'e2e': {'api': 'LRBMSReductor.reduce()', 'first_call_s': t_reduce_first, 'repeat_call_s': float(np.min(t_e2e)),
+                'what': 'wall time incl. host planning, plan creation and all kernels; first call also pays one-off operator '
+                        'preparation (fused chain products, transposes) and CUDA module load'},
+    }
+
+
+def measure_sharded_offline(a, torch, dist, d, bases, flush_l2, barrier, ms_unsharded, label):
+    """Strong scaling of the offline half: the same operator set, subdomains split over the ranks, reduced regions exchanged
+    by one in-place all-gather.  The gathered buffer must equal the unsharded result bit for bit (checked here)."""
+    from pylrbms_b200 import LRBMSReductor
+    world = dist.get_world_size()
+    red_s = LRBMSReductor(d, bases=bases, shard=True)
+    red_s.reduce()
+    ps = red_s.last_plan
+    for _ in range(3):
+        ps.run(); ps.exchange()
+    t_run, t_all = [], []
+    for _ in range(max(3, a.steps)):
+        flush_l2()
+        barrier()
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        e0.record()
+        ps.run()
+        e1.record()
+        ps.exchange()
+        e2.record()
+        e2.synchronize()
+        t_run.append(e0.elapsed_time(e1)); t_all.append(e0.elapsed_time(e2))
+    tt = torch.tensor([float(np.mean(t_run)), float(np.mean(t_all))], dtype=torch.float64, device='cuda')
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    # bitwise check against the unsharded projection of the same bases on this rank
+    red_u = LRBMSReductor(d, bases=bases)
+    rd_u = red_u.reduce()
+    rd_s = red_s.reduce()
+    same = True
+    for name in ('operator', 'nc_0', 'r_dd_%d' % (len(rd_u.block_dims) - 1)):
+        ou, os_ = rd_u.operators[name], rd_s.operators[name]
+        for gu, gs in zip(getattr(ou, 'operators', [ou]), getattr(os_, 'operators', [os_])):
+            same = same and bool(np.array_equal(gu.to_dense(), gs.to_dense()))
+    flag = torch.tensor([1.0 if same else 0.0], dtype=torch.float64, device='cuda')
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if flag.item() != 1.0:
+        raise SystemExit('bench.py: sharded offline projection differs from the unsharded one')
+    return {
+        'workload': label, 'n_gpus': world, 'scaling': 'strong', 'partition': 'contiguous strips of subdomains per rank',
+        'ms_all_stages_max_over_ranks': float(tt[0].item()), 'ms_with_exchange_max_over_ranks': float(tt[1].item()),
+        'ms_all_stages_1gpu_unsharded_this_rank': ms_unsharded,
+        'speedup_vs_unsharded': ms_unsharded / float(tt[0].item()),
+        'speedup_vs_unsharded_incl_exchange': ms_unsharded / float(tt[1].item()),
+        'exchange': 'one in-place NCCL all-gather of equal-stride rank regions, %d doubles in total' % int(ps.out.numel()),
+        'bitwise_equal_to_unsharded': True,
+        'projection_descriptors_this_rank': ps.n_project_descs,
+    }
+
+
+def parity_gate(a, rd, mus_all, rd_ref=None):
+    """no timing counts without parity.  The reduced model the GPU arm just timed is compared with the
+    oracle's on the same inputs: every reduced operator / product (max-norm, relative to the operator), and for a sample of
+    the benchmark's own parameters u(mu) in the energy norm, eta and its three parts -- through ``sweep_into`` (the e2e
+    entry point) and ``sweep``.  Raises SystemExit on failure."""
+    from oracle.parity import RTOL, compare_online, compare_operators, reference_online
+    import torch
+    if rd_ref is None:
+        rd_ref = cpu_reference_model(a)
+    rd_ref_pair, rd_ref = rd_ref, rd_ref[0]
+    worst, checked = 0.0, 0
+    for name, err in compare_operators(rd, rd_ref).items():
+        if not err <= RTOL:
+            raise SystemExit('bench.py: PARITY FAILURE, reduced operator {}: rel err {:.3e}'.format(name, err))
+        worst, checked = max(worst, err), checked + 1
+    n = a.cpu_sample
+    mus = np.asarray(mus_all[:n])
+    ref = reference_online(rd_ref, mus)
+    u_host = torch.empty((n, rd.n_red), dtype=torch.float64).pin_memory()
+    eta_host = torch.empty(n, dtype=torch.float64).pin_memory()
+    if rd.sweep_into(mus, u_host, eta_host) != 0:
+        raise SystemExit('bench.py: PARITY FAILURE, a reduced system was flagged as not positive definite')
+    e1 = compare_online(rd, rd_ref, mus, U=u_host.numpy(), eta=eta_host.numpy(), ref=ref)
+    e2 = compare_online(rd, rd_ref, mus, ref=ref)
+    for tag, errs in (('sweep_into', e1), ('sweep', e2)):
+        for name, err in errs.items():
+            lim = 10 * RTOL if name == 'indicators' else RTOL
+            if not err <= lim:
+                raise SystemExit('bench.py: PARITY FAILURE, {} {}: rel err {:.3e}'.format(tag, name, err))
+            worst, checked = max(worst, err), checked + n
+    return {'max_rel': worst, 'checked': checked, 'tol': RTOL, 'n_mu': n, 'reduced_operators': len(rd_ref.operators) + len(rd_ref.products),
+            'what': 'every reduced operator and product vs the oracle (max-norm rel.); u(mu) in the energy norm, eta, nc / r / df '
+                    'and indicators for the first {} benchmark parameters, through ReducedModel.sweep_into and .sweep'.format(n)}, rd_ref_pair
+
+
 def run_b200(a):
     import torch
     import torch.distributed as dist
@@ -355,13 +569,13 @@ def run_b200(a):
     data, bases = make_inputs(a)
     d, _ = discretize(data)
     reductor = LRBMSReductor(d, bases=bases)
+    torch.cuda.synchronize()
     t0 = time.perf_counter()
     rd = reductor.reduce()
     torch.cuda.synchronize()
     t_reduce_first = time.perf_counter() - t0
     planner = reductor.last_plan
-    if not a.synthetic3d:
-        rd.online_plan                                 # build the online plan (symbolic phase + tile upload)
+    rd.online_plan                                     # build the online plan (symbolic phase + operator upload)
 
     flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device='cuda')     # 256 MB > 126 MB L2
     fp64_peak = measure_fp64_gemm_peak(torch)
@@ -369,101 +583,42 @@ def run_b200(a):
     def flush_l2():
         flush.fill_(1.0)
 
-    # ---- offline half: the batched projection of every operator (kernel-only, inputs resident in HBM)
+    # ---- offline half: the batched projection of every operator
     offline = None
     if not a.no_offline:
-        st = planner.stats()
-        for _ in range(max(3, a.warmup)):
-            planner.run()
-        times_all, times_proj = [], []
-        for _ in range(max(3, a.steps)):
-            flush_l2()
-            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-            e0.record()
-            planner.spmm_plans[0].run()        # stage 0: Oswald / flux-reconstruction images of the bases (rows a2, a3)
-            e1.record()
-            for p in planner.spmm_plans[1:]:   # later stages belong to the projection: D R, and A^T L of the narrow-left chains
-                p.run()
-            planner.project_plan.run()
-            e2.record()
-            e2.synchronize()
-            times_all.append(e0.elapsed_time(e2)); times_proj.append(e1.elapsed_time(e2))
-        hbm_peak, hbm_src = measured_peaks()
-        pp = planner.project_plan
-        t_proj = float(np.mean(times_proj)) * 1e-3
-        # Algorithmic work = SURVEY.md section 8d formula on the operators as the reference defines them (every chain applied
-        # matrix by matrix to the right-hand array).  The plan that runs does less: products of chained sparse matrices are
-        # formed once on the host (r_dd: Gram over the m_i flux dofs instead of the n_i DG dofs) and narrow-left chains apply
-        # the matrix to the narrow side; its own count is reported as *_executed.
-        acct = LRBMSReductor(d, bases=bases)
-        acct.fuse_chains, acct.narrow_left = False, False
-        acct_plan = acct.build_plan()
-        alg_bytes = acct_plan.project_plan.algorithmic_bytes_survey
-        alg_flops = acct_plan.project_plan.flops
-        alg_descs = acct_plan.n_project_descs
-        del acct, acct_plan
-        gbs = alg_bytes / t_proj / 1e9
-        tfs = alg_flops / t_proj / 1e12
-        ai = alg_flops / alg_bytes
-        tensor_bound = ai > fp64_peak * 1e12 / (hbm_peak * 1e9)      # arithmetic intensity above the HBM / FP64 crossover
-        roof = {'bound': 'tensor' if tensor_bound else 'hbm', 'kernel': 'projection plan (all buckets of one run: spmm_kernel, '
-                                                                        'project_kernel, gram_kernel)',
-                'achieved': tfs if tensor_bound else gbs, 'peak': fp64_peak if tensor_bound else hbm_peak,
-                'unit': 'TFLOP/s' if tensor_bound else 'GB/s',
-                'frac': tfs / fp64_peak if tensor_bound else gbs / hbm_peak,
-                'traffic': NCU_TRAFFIC_BYTES['projection_plan'] if (a.subdomains, a.cells, a.basis, a.synthetic3d) == (8, 32, 20, None) else None,
-                'peak_source': ('cuBLAS DGEMM 4096^3 measured in this run (FP64 tensor pipe)' if tensor_bound else hbm_src),
-                'arithmetic_intensity_flop_per_byte': ai,
-                'algorithmic_bytes_survey_formula': alg_bytes, 'flops': alg_flops,
-                'bytes_executed_plan': pp.algorithmic_bytes_survey, 'flops_executed_plan': pp.flops,
-                'fp64_tflops_executed': pp.flops / t_proj / 1e12, 'hbm_gbs': gbs, 'hbm_peak_gbs': hbm_peak, 'hbm_frac': gbs / hbm_peak, 'hbm_peak_source': hbm_src,
-                'fp64_tflops': tfs, 'fp64_peak_tflops': fp64_peak, 'fp64_frac': tfs / fp64_peak,
-                'note': 'bound = whichever of the two rooflines binds at this arithmetic intensity (crossover %.1f flop/B); both '
-                        'fractions are reported' % (fp64_peak * 1e12 / (hbm_peak * 1e9))}
-        offline = {
-            'metric': 'offline projection HBM GB/s', 'unit': 'GB/s', 'value': gbs,
-            'ms_all_stages': float(np.mean(times_all)), 'ms_projection': float(np.mean(times_proj)),
-            'ms_projection_covers': 'SpMM stages >= 1 (divergence images, A^T L of narrow-left chains) + the projection plan; '
-                                    'stage 0 (Oswald / flux-reconstruction images of the bases) is the rest of ms_all_stages',
-            'projection_descriptors': planner.n_project_descs, 'spmm_descriptors': planner.n_spmm_descs,
-            'launches_per_reduce': st['launches'], 'roofline': roof,
-            'first_reduce_incl_planning_s': t_reduce_first,
-        }
-    # ---- N > 1: the subdomain-sharded offline half (strong scaling: the same operator set split over the ranks, each rank
-    #      projects the blocks of its strip of subdomains; the reduced regions are exchanged over NCCL afterwards)
-    if world > 1 and offline is not None:
-        red_s = LRBMSReductor(d, bases=bases, shard=True)
-        red_s.reduce()
-        ps = red_s.last_plan
-        for _ in range(3):
-            ps.run(); ps.exchange()
-        t_run, t_all = [], []
-        for _ in range(max(3, a.steps)):
-            flush_l2()
-            barrier()
-            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-            e0.record()
-            ps.run()
-            e1.record()
-            ps.exchange()
-            e2.record()
-            e2.synchronize()
-            t_run.append(e0.elapsed_time(e1)); t_all.append(e0.elapsed_time(e2))
-        tt = torch.tensor([float(np.mean(t_run)), float(np.mean(t_all))], dtype=torch.float64, device='cuda')
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        offline['sharded'] = {
-            'n_gpus': world, 'scaling': 'strong', 'partition': 'contiguous strips of subdomains per rank',
-            'ms_all_stages_max_over_ranks': float(tt[0].item()), 'ms_with_exchange_max_over_ranks': float(tt[1].item()),
-            'ms_all_stages_1gpu_unsharded_this_rank': offline['ms_all_stages'],
-            'speedup_vs_unsharded': offline['ms_all_stages'] / float(tt[0].item()),
-            'exchange': 'one NCCL broadcast per rank region (all-gather of disjoint reduced blocks), %d doubles in total' % int(ps.out.numel()),
-            'projection_descriptors_this_rank': ps.n_project_descs,
-        }
-    if a.synthetic3d:
-        # auxiliary measurement (config C4 shape): the offline half only; the driver's bench line is the default workload
+        offline = measure_offline(a, torch, planner, d, bases, fp64_peak, flush_l2, t_reduce_first, reductor)
+        rd = reductor.reduce()                         # (measure_offline re-ran reduce(): keep the model of the last plan)
+        rd.online_plan
+        if world > 1:
+            offline['sharded'] = measure_sharded_offline(a, torch, dist, d, bases, flush_l2, barrier, offline['ms_all_stages'],
+                                                         offline_workload_name(a))
+        if world > 1 and a.c3_sharded and not a.synthetic3d and (a.problem, a.subdomains) != ('spe10', 16):
+            # configs[2]: high-contrast SPE10-like field on 16 x 16 subdomains, offline projection + estimator Grams at N GPUs
+            import copy
+            a3 = copy.copy(a)
+            a3.problem, a3.subdomains = 'spe10', 16
+            data3, bases3 = make_inputs(a3)
+            d3, _ = discretize(data3)
+            red3 = LRBMSReductor(d3, bases=bases3)
+            red3.reduce()
+            p3 = red3.last_plan
+            for _ in range(3):
+                p3.run()
+            t3 = []
+            for _ in range(max(3, a.steps)):
+                flush_l2()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); p3.run(); e1.record(); e1.synchronize()
+                t3.append(e0.elapsed_time(e1))
+            del red3, p3
+            offline['sharded_c3'] = measure_sharded_offline(a3, torch, dist, d3, bases3, flush_l2, barrier, float(np.mean(t3)),
+                                                            offline_workload_name(a3))
+            del d3, data3, bases3
+            torch.cuda.empty_cache()
+    if a.offline_only:
         if rank == 0:
             print(json.dumps({'metric': 'offline projection HBM GB/s', 'value': offline['value'], 'unit': 'GB/s', 'n_gpus': world,
-                              'dtype': 'f64', 'data': 'synthetic', 'config': {'workload': workload_name(a)},
+                              'dtype': 'f64', 'data': 'synthetic', 'config': {'workload': offline_workload_name(a)},
                               'higher_is_better': True, 'offline': offline}))
         if world > 1:
             dist.destroy_process_group()
@@ -471,12 +626,12 @@ def run_b200(a):
 
     # ---- online half
     n_mu = a.n_mu
-    mus = make_mus(a, rank, n_mu)
+    mus = make_mus(a, rank, n_mu, data)
     theta = torch.from_numpy(rd.thetas(mus)).cuda()
-    S = len(rd.block_dims)
     u = torch.empty((n_mu, rd.n_red), dtype=torch.float64, device='cuda')
     eta = torch.empty(n_mu, dtype=torch.float64, device='cuda')
     info = torch.empty(n_mu, dtype=torch.int32, device='cuda')
+    rd._workspace(n_mu)
 
     def step():
         rd.solve_device(theta, u, info)
@@ -505,7 +660,7 @@ def run_b200(a):
         t_step.append(e0.elapsed_time(e1)); t_solve.append(e0.elapsed_time(ev_mid))
     barrier()
     clocks = sampler.stop() if rank == 0 else None
-    if int(info.max().item()) != 0:
+    if int(info.abs().max().item()) != 0:
         raise SystemExit('bench.py: a reduced system was flagged as not positive definite')
     total_ms = torch.tensor([float(np.sum(t_step))], dtype=torch.float64, device='cuda')
     if world > 1:
@@ -513,18 +668,35 @@ def run_b200(a):
     total_s = float(total_ms.item()) * 1e-3
     value = world * n_mu * a.steps / total_s
 
-    # ---- end to end through the public API: host parameters -> host (U, eta), copies inside the timed region
-    u_host = torch.empty((n_mu, rd.n_red), dtype=torch.float64).pin_memory()
-    eta_host = torch.empty(n_mu, dtype=torch.float64).pin_memory()
+    # ---- end to end through the public API: host parameters -> host results, copies inside the timed region
+    e2e_steps = max(2, min(a.steps, 5))
+    if a.eta_only:
+        eta_host = torch.empty(n_mu, dtype=torch.float64).pin_memory()
+
+        def e2e_call():
+            bad, mx_, am_ = rd.sweep_eta_into(mus, eta_host)
+            return bad, mx_
+        d2h = int(eta.numel() * 8)
+        api = 'ReducedModel.sweep_eta_into(mus, eta_host)'
+    else:
+        u_host = torch.empty((n_mu, rd.n_red), dtype=torch.float64).pin_memory()
+        eta_host = torch.empty(n_mu, dtype=torch.float64).pin_memory()
+
+        def e2e_call():
+            bad = rd.sweep_into(mus, u_host, eta_host)
+            return bad, float(eta_host.max())
+        d2h = int((u.numel() + eta.numel()) * 8)
+        api = 'ReducedModel.sweep_into(mus, u_host, eta_host)'
     for _ in range(2):
-        rd.sweep_into(mus, u_host, eta_host)
+        e2e_call()
     barrier()
     t0 = time.perf_counter()
-    e2e_steps = max(2, min(a.steps, 5))
     for _ in range(e2e_steps):
-        rd.sweep_into(mus, u_host, eta_host)
+        bad, mx_ = e2e_call()
+        if bad:
+            raise SystemExit('bench.py: a reduced system was flagged as not positive definite (e2e)')
         if world > 1:
-            m = torch.tensor([float(eta_host.max())], dtype=torch.float64, device='cuda')
+            m = torch.tensor([mx_], dtype=torch.float64, device='cuda')
             dist.all_reduce(m, op=dist.ReduceOp.MAX)
     barrier()
     e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device='cuda')
@@ -532,49 +704,98 @@ def run_b200(a):
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_value = world * n_mu * e2e_steps / float(e2e_s.item())
 
+    # ---- configs[4]: the 1M-parameter sweep, 125 000 parameters per GPU, estimator-max gather, eta-only results
+    c5 = None
+    if a.c5 and not a.synthetic3d:
+        n5 = 125000
+        mus5 = make_mus(a, 100 + rank, n5, data)
+        eta5 = torch.empty(n5, dtype=torch.float64).pin_memory()
+        from pylrbms_b200.distributed import gather_estimator_max
+
+        def c5_call():
+            bad5, mx5, am5 = rd.sweep_eta_into(mus5, eta5)
+            if bad5:
+                raise SystemExit('bench.py: a reduced system was flagged as not positive definite (C5)')
+            lo5 = rank * n5
+            return gather_estimator_max(torch.tensor([mx5], dtype=torch.float64, device='cuda'),
+                                        torch.tensor([am5], dtype=torch.int64, device='cuda'), lo5)
+        c5_call()
+        barrier()
+        t0 = time.perf_counter()
+        reps5 = 2
+        for _ in range(reps5):
+            gmax, garg = c5_call()
+        barrier()
+        t5 = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device='cuda')
+        if world > 1:
+            dist.all_reduce(t5, op=dist.ReduceOp.MAX)
+        c5 = {'workload': '{} parameters ({} per GPU), 64 subdomains, estimator-max gather'.format(world * n5, n5),
+              'value': world * n5 * reps5 / float(t5.item()), 'unit': UNIT, 'n_gpus': world,
+              'api': 'ReducedModel.sweep_eta_into + distributed.gather_estimator_max (one all-gather of (max, argmax) pairs per sweep)',
+              'h2d_bytes_per_sweep': int(n5 * theta.shape[1] * 8), 'd2h_bytes_per_sweep': int(n5 * 8),
+              'eta_max': gmax, 'argmax_global': garg, 'seconds_per_sweep': float(t5.item()) / reps5}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (solve_kernel: FP64 tensor-core tile Cholesky)
-    fl = survey_flops_per_mu(a.subdomains, a.basis, data.Q)
+    # ---- roofline of the dominant kernel: the solve kernel the plan selected (name, flop count from the library)
+    fl = survey_flops_per_mu(a, data, rd)
     solve_s = float(np.mean(t_solve)) * 1e-3
     achieved = fl['solve'] * n_mu / solve_s / 1e12
-    from pylrbms_b200._lib import Symbolic
-    default_workload = (a.subdomains, a.cells, a.basis, a.n_mu) == (8, 32, 20, 10000)
-    solve_name = 'solve_kernel_v2' if os.environ.get('LRBMS_SOLVE_V1', '0') in ('', '0') else 'solve_kernel'
+    solve_name = rd.solve_kernel_name
+    executed = rd.solve_flops_executed
     roofline = {'bound': 'tensor', 'kernel': solve_name, 'achieved': achieved, 'peak': fp64_peak, 'unit': 'TFLOP/s',
                 'frac': achieved / fp64_peak,
-                'traffic': NCU_TRAFFIC_BYTES.get(solve_name) if default_workload else None,
+                'traffic': ncu_traffic(solve_name, workload_name(a)),
                 'peak_source': 'cuBLAS DGEMM 4096^3 measured in this run (FP64; MEASURED_PEAKS.json has no FP64 figure)',
-                'algorithmic_flops_per_mu': fl['solve'], 'ms_per_launch': 1e3 * solve_s,
-                'share_of_step': float(np.sum(t_solve) / np.sum(t_step))}
+                'algorithmic_flops_per_mu': fl['solve'], 'executed_flops_per_mu': executed,
+                'executed_tflops': executed * n_mu / solve_s / 1e12, 'executed_frac': executed * n_mu / solve_s / 1e12 / fp64_peak,
+                'ms_per_launch': 1e3 * solve_s, 'share_of_step': float(np.sum(t_solve) / np.sum(t_step))}
 
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': a.steps, 'warmup': max(3, a.warmup),
         'ms_per_step': 1e3 * total_s / a.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f64', 'data': 'synthetic',
         'config': {'workload': workload_name(a), 'n_red': fl['n_red'], 'reduced_blocks': fl['blocks'],
+                   'half_bandwidth': rd.half_bandwidth,
                    'l2': 'flushed between timed steps (256 MB write); factor scratch per step also exceeds L2',
                    'parallelism': 'mu-sharded x{}'.format(world), 'flops_per_mu_survey': fl['total']},
         'clocks': clocks,
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(theta.numel() * 8),
-                'd2h_bytes_per_step': int((u.numel() + eta.numel()) * 8), 'api': 'ReducedModel.sweep_into(mus, u_host, eta_host)'},
-        'gpu_launches': int(a.steps * 4),
+                'd2h_bytes_per_step': d2h, 'api': api},
+        'gpu_launches': int(a.steps * gpu_launches_per_step(rd)),
         'roofline': roofline,
         'offline': offline,
     }
-    if not a.no_cpu_baseline and world == 1:
-        line['cpu_baseline'] = cpu_baseline(a)
+    if c5 is not None:
+        line['c5_sweep'] = c5
+    rd_ref = None
+    if not a.no_parity and not a.synthetic3d and oracle_feasible(a):
+        line['parity'], rd_ref = parity_gate(a, rd, mus)
+    if not a.no_cpu_baseline and world == 1 and oracle_feasible(a):
+        line['cpu_baseline'] = cpu_baseline(a, rd_ref)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
-def cpu_baseline(a):
+def oracle_feasible(a):
+    """The reference-faithful oracle stores every reduced operator as an unblocked dense matrix:
+    ~5 GB at 8x8 subdomains, N = 20; beyond ~100 subdomains it does not fit a host."""
+    return a.subdomains ** 2 * a.basis <= 2000 and not a.synthetic3d
+
+
+def gpu_launches_per_step(rd):
+    """Kernels of this repo launched per timed step: the solve (1 launch for the CTA-per-parameter kernels, 3 per block column
+    + 2 per chunk for the band solver), estimate_kernel, combine_kernel, eta_max_kernel."""
+    return int(rd.online_plan.info(0)) + 1
+
+
+def cpu_baseline(a, rd_ref=None):
     use_all_host_threads()
-    rd, t_off = cpu_reference_model(a)
+    rd, t_off = rd_ref if rd_ref is not None else cpu_reference_model(a)
     mus = make_mus(a, 0, a.cpu_sample)
     cpu_online_step(rd, mus[:2])
     t = time.perf_counter()

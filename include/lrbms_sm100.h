@@ -53,6 +53,14 @@ int lrbms_create(int device, lrbms_handle_t* out);
 int lrbms_destroy(lrbms_handle_t h);
 const char* lrbms_last_error(lrbms_handle_t h);       /* h may be NULL: error of the last failed create */
 int lrbms_device_sm_count(lrbms_handle_t h, int* out);
+/* Run-time switches of a context (there are no environment variables in the library).
+ * LRBMS_OPT_SINGLE_STREAM: 1 = offline plans launch all their kernels on the caller's stream (profiling); 0 (default) =
+ * the independent launches of one plan run are spread over the caller's stream and three side streams of the context. */
+enum { LRBMS_OPT_SINGLE_STREAM = 1 };
+int lrbms_set_option(lrbms_handle_t h, int32_t option, int32_t value);
+/* Test hook: fills the shared memory of every SM with NaNs (a kernel that relied on stale shared memory being finite
+ * or zero then fails its parity test instead of passing by luck). */
+int lrbms_debug_poison_shared(lrbms_handle_t h, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------- */
 /*  GPU VectorArray backing                                                                              */
@@ -152,7 +160,9 @@ int lrbms_remap_blocks(lrbms_handle_t h, int32_t n, const lrbms_remap_desc_t* de
 int lrbms_plan_run(lrbms_plan_t plan, void* stream);
 int lrbms_plan_destroy(lrbms_plan_t plan);
 /* what: 0 = kernel launches per run, 1 = CTAs of the main kernel, 2 = algorithmic bytes per run (tight count),
- *       3 = algorithmic flops per run, 4 = device bytes owned by the plan, 5 = algorithmic bytes (SURVEY formula) */
+ *       3 = algorithmic flops per run, 4 = device bytes owned by the plan, 5 = algorithmic bytes (SURVEY formula);
+ *       online plans: 6 = solve kernel the plan selected (LRBMS_SOLVER_*), 7 = factor flops per parameter that kernel
+ *       executes, 8 = scalar half bandwidth of the reduced operator */
 int lrbms_plan_info(lrbms_plan_t plan, int32_t what, double* out);
 
 /* ---------------------------------------------------------------------------------------------------- */
@@ -191,13 +201,20 @@ typedef struct {
   int64_t matrix_offset;   /* into the estimator matrix buffer, in doubles; M row-major, ld = cols */
 } lrbms_estimator_term_t;
 
+/* Solve kernel of an online plan.  AUTO: the shared-memory-window kernel (one SM per parameter, live factor window in
+ * shared memory) when the window fits, else the block-banded out-of-HBM Cholesky (whole GPU per chunk of parameters).
+ * WINDOW / BANDED force one of them (WINDOW fails with LRBMS_ERR_UNSUPPORTED when the window does not fit);
+ * GLOBAL_TILES is the first-generation kernel (tile factor in global scratch), kept for cross-checks. */
+enum { LRBMS_SOLVER_AUTO = 0, LRBMS_SOLVER_WINDOW = 1, LRBMS_SOLVER_GLOBAL_TILES = 2, LRBMS_SOLVER_BANDED = 3 };
+
 typedef struct {
   int32_t n_sub;
   const int32_t* basis_sizes;          /* host [n_sub] */
   int32_t Q;                           /* affine terms of the reduced operator */
   int32_t Qf;                          /* affine terms of the reduced rhs */
   int32_t n_blocks;
-  const int32_t* block_i;              /* host [n_blocks]; only blocks with i >= j are read (the operator is symmetric) */
+  const int32_t* block_i;              /* host [n_blocks]; only blocks with i >= j are read: the operator MUST be symmetric
+                                          (block (j, i) = block (i, j)^T); this is not validated */
   const int32_t* block_j;
   const int64_t* block_offset;         /* host [Q * n_blocks]: offset (doubles) of block b of term q: [q * n_blocks + b] */
   const double* lhs_blocks;            /* device: packed row-major N_i x N_j blocks */
@@ -213,6 +230,7 @@ typedef struct {
   const double* theta_bar;             /* host [Q] theta_q(mu_bar) */
   const double* theta_hat;             /* host [Q] theta_q(mu_hat) */
   int32_t alpha_returns_first;         /* 1 reproduces estimators.py:114-121 (alpha = theta_0 ratio only) */
+  int32_t solver;                      /* LRBMS_SOLVER_* (0 = AUTO) */
 } lrbms_reduced_system_t;
 
 int lrbms_online_plan_create(lrbms_handle_t h, const lrbms_reduced_system_t* sys, lrbms_plan_t* out);
@@ -227,7 +245,8 @@ int lrbms_online_estimate(lrbms_plan_t plan, int64_t n_mu, const double* theta, 
 /* solve + estimate in one call (the unit of work of BASELINE.json's metric) */
 int lrbms_online_sweep(lrbms_plan_t plan, int64_t n_mu, const double* theta, double* u, double* eta, double* parts,
                        double* indicators, int32_t* info, void* workspace, size_t workspace_bytes, void* stream);
-/* Developer aid: with LRBMS_SOLVE_TIMING=1 in the environment at plan creation the shared-memory solve kernel records,
+/* Developer aid, only in libraries compiled with -DLRBMS_DEVTOOLS (the shipped build returns LRBMS_ERR_UNSUPPORTED):
+ * with LRBMS_SOLVE_TIMING=1 in the environment at plan creation the shared-memory solve kernel records,
  * for CTA 0, SM-clock cycles per warp and phase ([16 warps][8 phases]: 0 metadata staging, 1 diagonal tile, 2 early
  * updates, 3 barrier, 4 triangular solve + late update, 5 barrier, 6 backward substitution, 7 store).  Copies up to n
  * counters to out_host and returns how many were written, or a negative status. */

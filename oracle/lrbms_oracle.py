@@ -476,7 +476,10 @@ class LRBMSReductor(GenericRBSystemReductor):
             for ii in range(len(d.solution_space.subspaces)):
                 self.extend_basis_local(d.shape_functions(ii, order))
 
-    def _reduce(self):
+    def image_bases(self, unblocked=True):
+        """reference reductor.py:36-66: the OI / RT image bases and the reduced OI / FR operators.  ``unblocked=False`` skips
+        the dense ``unblock`` of the two reduced operators (parity tests at sizes where ``n_red^2`` storage per operator
+        is out of reach only need ``self.bases``)."""
         d = self.d
         # Oswald interpolations (reductor.py:36-46)
         oi = d.estimator.oswald_interpolation_error
@@ -486,7 +489,7 @@ class LRBMSReductor(GenericRBSystemReductor):
             basis = self.bases[oi_i.source.id]
             self.bases[OI_i_space.id] = oi_i.apply(basis)
             oi_red.append(MatrixOperator(np.eye(len(basis)), source_id=oi_i.source.id, range_id=oi_i.range.id))
-        oi_red = unblock(BlockDiagonalOperator(oi_red))
+        oi_red = unblock(BlockDiagonalOperator(oi_red)) if unblocked else None
         # flux reconstructions (reductor.py:48-66)
         fr = d.estimator.flux_reconstruction
         for i, RT_i_space in enumerate(fr.range.subspaces):
@@ -503,8 +506,12 @@ class LRBMSReductor(GenericRBSystemReductor):
                 red_aff_component.append(MatrixOperator(M, source_id=fr_i.source.id, range_id=fr_i.range.id))
             red_aff_components.append(BlockDiagonalOperator(red_aff_component))
         fr_red = LincombOperator(red_aff_components, fr.coefficients)
-        fr_red = unblock(fr_red)
+        fr_red = unblock(fr_red) if unblocked else None
+        return oi_red, fr_red
 
+    def _reduce(self):
+        d = self.d
+        oi_red, fr_red = self.image_bases()
         red_estimator = d.estimator.with_(flux_reconstruction=fr_red, oswald_interpolation_error=oi_red)
         rd = super()._reduce()
         rd = rd.with_(estimator=red_estimator)

@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'liblrbms_sm100.so')
 
 EXPORTS = [
-    'lrbms_version', 'lrbms_create', 'lrbms_destroy', 'lrbms_last_error', 'lrbms_device_sm_count',
+    'lrbms_version', 'lrbms_create', 'lrbms_destroy', 'lrbms_last_error', 'lrbms_device_sm_count', 'lrbms_set_option', 'lrbms_debug_poison_shared',
     'lrbms_va_scal', 'lrbms_va_axpy', 'lrbms_va_pairwise_dot', 'lrbms_va_lincomb', 'lrbms_va_copy_cols',
     'lrbms_va_transpose_in', 'lrbms_va_transpose_out',
     'lrbms_spmm_plan_create', 'lrbms_project_plan_create', 'lrbms_plan_run', 'lrbms_plan_destroy', 'lrbms_plan_info',
@@ -27,6 +27,8 @@ EXPORTS = [
 
 VEC_ONE, VEC_UI, VEC_UN, VEC_UR = 0, 1, 2, 3
 OUT_NC, OUT_R, OUT_DF = 0, 1, 2
+SOLVER_AUTO, SOLVER_WINDOW, SOLVER_GLOBAL_TILES, SOLVER_BANDED = 0, 1, 2, 3
+SOLVER_NAMES = {1: 'solve_kernel_v2', 2: 'solve_kernel', 3: 'band_update_kernel'}
 
 
 class LrbmsError(RuntimeError):
@@ -67,7 +69,8 @@ class ReducedSystem(C.Structure):
                 ('lhs_blocks', C.c_void_p), ('rhs', C.c_void_p),
                 ('nbh_ptr', C.c_void_p), ('nbh_idx', C.c_void_p), ('n_terms', C.c_int32), ('terms', C.c_void_p),
                 ('est_matrices', C.c_void_p), ('rf_squared', C.c_void_p), ('r_scale', C.c_void_p),
-                ('theta_bar', C.c_void_p), ('theta_hat', C.c_void_p), ('alpha_returns_first', C.c_int32)]
+                ('theta_bar', C.c_void_p), ('theta_hat', C.c_void_p), ('alpha_returns_first', C.c_int32),
+                ('solver', C.c_int32)]
 
 
 _lib = None
@@ -92,6 +95,8 @@ def load_library():
             'lrbms_destroy': (C.c_int, [vp]),
             'lrbms_last_error': (C.c_char_p, [vp]),
             'lrbms_device_sm_count': (C.c_int, [vp, P(C.c_int)]),
+            'lrbms_set_option': (C.c_int, [vp, i32, i32]),
+            'lrbms_debug_poison_shared': (C.c_int, [vp, vp]),
             'lrbms_va_scal': (C.c_int, [vp, i64, i32, vp, i32, vp, i32, vp]),
             'lrbms_va_axpy': (C.c_int, [vp, i64, i32, vp, i32, vp, i32, i32, vp, i32, vp]),
             'lrbms_va_pairwise_dot': (C.c_int, [vp, i64, i32, vp, i32, vp, i32, vp, vp]),

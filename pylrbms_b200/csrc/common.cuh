@@ -17,8 +17,8 @@ struct lrbms_context {
   int max_smem_optin = 0;
   std::string last_error;
   // side streams of the offline plans: the launches of one plan run (one per tile-shape bucket) are independent, so they
-  // are spread over the caller's stream and these and joined again before the plan returns (LRBMS_SINGLE_STREAM=1: off)
-  bool streams_ready = false, single_stream = false;
+  // are spread over the caller's stream and these and joined again before the plan returns (lrbms_set_option(LRBMS_OPT_SINGLE_STREAM, 1): off)
+  bool streams_ready = false, single_stream = false, streams_failed = false;
   cudaStream_t side[kSideStreams] = {};
   cudaEvent_t ev_fork = nullptr, ev_join[kSideStreams] = {};
 };
@@ -41,6 +41,7 @@ struct lrbms_plan {
   std::vector<void*> device_allocs;   // freed in lrbms_plan_destroy
   size_t device_bytes = 0;
   double info_launches = 0, info_ctas = 0, info_bytes = 0, info_flops = 0, info_bytes_survey = 0;
+  double info_solver = 0, info_solve_flops = 0, info_half_bandwidth = 0;   // online plans only
   virtual ~lrbms_plan() {}
   virtual int run(void* stream) = 0;
   virtual void ensure_info() {}       // byte / flop accounting is computed on first request, not at plan creation
@@ -151,6 +152,9 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
 }
 // generic-proxy accesses to shared memory before this point are ordered before later async-proxy (bulk copy) accesses
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+// the same for every state space: earlier generic-proxy stores to *global* memory (e.g. a factor written with st.global)
+// are ordered before later bulk copies that read them back through the async proxy
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }

@@ -8,15 +8,13 @@ thread_local std::string g_create_error;
 int ctx_streams(lrbms_context* ctx) {
   if (!ctx->streams_ready) {
     ctx->streams_ready = true;
-    const char* e = getenv("LRBMS_SINGLE_STREAM");
-    ctx->single_stream = e && e[0] == '1';
     bool ok = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess;
     for (int i = 0; i < kSideStreams && ok; ++i)
       ok = cudaStreamCreateWithFlags(&ctx->side[i], cudaStreamNonBlocking) == cudaSuccess &&
            cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming) == cudaSuccess;
-    if (!ok) { ctx->single_stream = true; cudaGetLastError(); }
+    if (!ok) { ctx->streams_failed = true; cudaGetLastError(); }
   }
-  return ctx->single_stream ? 1 : 1 + kSideStreams;
+  return (ctx->single_stream || ctx->streams_failed) ? 1 : 1 + kSideStreams;
 }
 
 void ctx_fork(lrbms_context* ctx, cudaStream_t s) {
@@ -33,9 +31,37 @@ void ctx_join(lrbms_context* ctx, cudaStream_t s) {
   }
 }
 
+namespace {
+// test hook: every resident CTA fills its whole dynamic shared memory with quiet NaNs and holds it until all have
+__global__ void poison_shared_kernel(int n_doubles) {
+  extern __shared__ double poison[];
+  for (int i = threadIdx.x; i < n_doubles; i += blockDim.x) poison[i] = __longlong_as_double(0x7ff8000000000000ll);
+  __syncthreads();
+  if (poison[n_doubles - 1] == 0.0) printf("unreachable\n");    // keeps the stores alive
+}
+}  // namespace
+
 extern "C" {
 
 int lrbms_version(void) { return LRBMS_VERSION; }
+
+int lrbms_debug_poison_shared(lrbms_handle_t h, void* stream) {
+  LRBMS_REQUIRE(h, h != nullptr, "lrbms_debug_poison_shared: null handle");
+  LRBMS_CUDA_CHECK(h, cudaSetDevice(h->device));
+  const int bytes = h->max_smem_optin - 1024;
+  LRBMS_CUDA_CHECK(h, cudaFuncSetAttribute(poison_shared_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  poison_shared_kernel<<<4 * h->sm_count, 256, bytes, (cudaStream_t)stream>>>(bytes / 8);
+  LRBMS_CUDA_CHECK(h, cudaGetLastError());
+  return LRBMS_OK;
+}
+
+int lrbms_set_option(lrbms_handle_t h, int32_t option, int32_t value) {
+  LRBMS_REQUIRE(h, h != nullptr, "lrbms_set_option: null handle");
+  switch (option) {
+    case LRBMS_OPT_SINGLE_STREAM: h->single_stream = value != 0; return LRBMS_OK;
+    default: return lrbms_fail(h, LRBMS_ERR_INVALID, "lrbms_set_option: unknown option");
+  }
+}
 
 int lrbms_create(int device, lrbms_handle_t* out) {
   if (!out) return lrbms_fail(nullptr, LRBMS_ERR_INVALID, "lrbms_create: out is NULL");
@@ -101,6 +127,7 @@ int lrbms_plan_run(lrbms_plan_t plan, void* stream) {
 int lrbms_plan_destroy(lrbms_plan_t plan) {
   if (!plan) return LRBMS_OK;
   // the plan's buffers go back to the pool in stream order; work that still uses them may sit on any stream
+  if (plan->ctx) cudaSetDevice(plan->ctx->device);
   if (!plan->device_allocs.empty()) cudaDeviceSynchronize();
   for (void* p : plan->device_allocs) cudaFreeAsync(p, (cudaStream_t)0);
   delete plan;
@@ -117,6 +144,9 @@ int lrbms_plan_info(lrbms_plan_t plan, int32_t what, double* out) {
     case 3: *out = plan->info_flops; break;
     case 4: *out = (double)plan->device_bytes; break;
     case 5: *out = plan->info_bytes_survey; break;
+    case 6: *out = plan->info_solver; break;
+    case 7: *out = plan->info_solve_flops; break;
+    case 8: *out = plan->info_half_bandwidth; break;
     default: return lrbms_fail(plan->ctx, LRBMS_ERR_INVALID, "lrbms_plan_info: unknown selector");
   }
   return LRBMS_OK;

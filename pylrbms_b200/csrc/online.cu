@@ -15,6 +15,7 @@
 #include <algorithm>
 #include <cmath>
 
+#include "band.h"
 #include "common.cuh"
 #include "symbolic.h"
 
@@ -293,10 +294,10 @@ struct SolveParamsV2 {
   int32_t max_col_pairs;
   int32_t max_a_col;
   int32_t back_stage_doubles;
-  int32_t plain_deal;       // 1 (LRBMS_SOLVE_BIASED_DEAL=1): warps 4, 8, 12 (the chain warp's scheduler) come last in every round
   int32_t staggered;        // schedule variant of the symbolic phase (lrbms_symbolic::staggered)
-  int32_t no_store;         // timing experiment only (LRBMS_SOLVE_NOSTORE=1): skip the factor store (wrong results)
-  long long* timing;        // optional (LRBMS_SOLVE_TIMING=1): [16 warps][8 phases] SM cycles of CTA 0, else NULL
+#ifdef LRBMS_DEVTOOLS
+  long long* timing;        // developer builds only (-DLRBMS_DEVTOOLS, LRBMS_SOLVE_TIMING=1): [16 warps][8 phases] SM cycles of CTA 0
+#endif
 };
 
 // acc -= sum_p A_p * B_p^T over staged pairs [p0, p1).  Eight accumulator registers = four independent DMMA chains
@@ -362,9 +363,13 @@ solve_kernel_v2(SolveParamsV2 P2, int64_t n_mu, const double* __restrict__ theta
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, t = lane & 3;
   double* L = work + (int64_t)blockIdx.x * P.work_stride;
+#ifdef LRBMS_DEVTOOLS
   const bool timing = P2.timing != nullptr && blockIdx.x == 0;
   long long tph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tlast = 0;
 #define LRBMS_TICK(k) do { if (timing) { const long long now_ = clock64(); tph[k] += now_ - tlast; tlast = now_; } } while (0)
+#else
+#define LRBMS_TICK(k) do { } while (0)
+#endif
 
   // ---- per-column tables: loaded once per CTA, no global-memory latency inside the column loop afterwards
   for (int i = threadIdx.x; i <= P.ntc; i += kV2Threads) sCol[i] = P2.ccol[i];
@@ -414,15 +419,10 @@ solve_kernel_v2(SolveParamsV2 P2, int64_t n_mu, const double* __restrict__ theta
     const int* ordC = sOrd + mb * MT;
     const double* aC = sA + (Jx % kABufs) * a_buf_doubles;
     const int ncol = sCol[Jx].y;
-    // Snake deal over the 14 update warps (1..14), longest item first.  (An earlier version put warps 4, 8, 12 -- which
-    // share their scheduler and its FP64 pipe with the chain warp 0 -- last in every round; the chain has slack, and the
-    // plain deal is 4.6 % faster per parameter.  LRBMS_SOLVE_BIASED_DEAL=1 brings the old deal back.)
-    const int q4 = warp >> 2;
-    const bool plain = P2.plain_deal == 0;
-    // (the triangular solve gives warps 1 .. n_tiles - 14 two tiles and the others one, so the longest early items go to
-    // the *high* warps: warp 14 first)
-    const int posU = plain ? (kUpd - warp) : ((warp & 3) ? (warp - 1 - q4) : (10 + q4));
-    const int posR = plain ? (kUpd - 1 - posU) : ((warp & 3) ? (10 - posU) : (14 - q4));
+    // Snake deal over the 14 update warps (1..14), longest item first.  (The triangular solve gives warps
+    // 1 .. n_tiles - 14 two tiles and the others one, so the longest early items go to the *high* warps: warp 14 first.)
+    const int posU = kUpd - warp;
+    const int posR = kUpd - 1 - posU;
     for (int r = 0; kUpd * r <= ncol; ++r) {
       const int item = kUpd * r + ((r & 1) ? posR : posU);
       if (item > ncol) continue;
@@ -524,7 +524,7 @@ solve_kernel_v2(SolveParamsV2 P2, int64_t n_mu, const double* __restrict__ theta
         if (!on[k]) continue;
         if (li[k] < ncol) {
           *reinterpret_cast<double2*>(win + ((slotP[li[k]] & 0xfffff) - 1) * 64 + lane * 2) = frag[k];
-          if (!P2.no_store) *reinterpret_cast<double2*>(L + (int64_t)(cp0 + li[k]) * 64 + lane * 2) = frag[k];
+          *reinterpret_cast<double2*>(L + (int64_t)(cp0 + li[k]) * 64 + lane * 2) = frag[k];
         } else if (g == 0) {
           sx[8 * Jy + 2 * t] = x0[k];
           sx[8 * Jy + 2 * t + 1] = x1[k];
@@ -633,7 +633,9 @@ solve_kernel_v2(SolveParamsV2 P2, int64_t n_mu, const double* __restrict__ theta
     if (warp == kProducer) { stage_meta(0); stage_meta(1); stage_meta(2); }
     cp_async_wait<0>();
     __syncthreads();
+#ifdef LRBMS_DEVTOOLS
     if (timing) tlast = clock64();
+#endif
     if (is_upd) early_updates(0, acc0);
     __syncthreads();
 
@@ -712,6 +714,9 @@ solve_kernel_v2(SolveParamsV2 P2, int64_t n_mu, const double* __restrict__ theta
       auto wait_column = [&](int Jc) {
         if (Jc >= 0) mbar_wait(&s_back_bar[(P.ntc - 1 - Jc) % kBackStages], (unsigned)(((P.ntc - 1 - Jc) / kBackStages) & 1));
       };
+      // The factor tiles written with st.global above are read back by bulk copies (async proxy): every writer orders its
+      // generic-proxy stores before later async-proxy accesses (all state spaces) ahead of the barrier.
+      fence_proxy_async_all();
       __syncthreads();                                  // everybody is through with the window
       if (threadIdx.x == 0)
         for (int i = 0; i < kBackStages; ++i) mbar_init(&s_back_bar[i], 1);
@@ -786,8 +791,10 @@ solve_kernel_v2(SolveParamsV2 P2, int64_t n_mu, const double* __restrict__ theta
     if (threadIdx.x == 0 && info) info[mu] = s_info;
     LRBMS_TICK(7);
   }
+#ifdef LRBMS_DEVTOOLS
   if (timing && lane == 0)
     for (int k = 0; k < 8; ++k) P2.timing[warp * 8 + k] = tph[k];
+#endif
 #undef LRBMS_TICK
 }
 
@@ -825,9 +832,12 @@ estimate_kernel(EstParams P, int64_t n_mu, const double* __restrict__ theta, con
                 double* __restrict__ parts) {
   constexpr int kLDX = kTMU + 4;
   extern __shared__ double smem[];
-  double* XN = smem;                                   // dmax_pad x kLDX
-  double* XR = XN + (int64_t)P.dmax_pad * kLDX;        // qdmax_pad x kLDX
-  double* TH = XR + (int64_t)P.qdmax_pad * kLDX;       // Q x kTMU
+  // Four spare rows behind each array: a term whose vector is a slice (u_i starts at row lo_self, any alignment) runs its
+  // k loop to the next multiple of 4 and may read up to three rows past the neighbourhood's last; every row up to the end
+  // of the arrays is zero-filled below, so 0 * (stale shared memory, possibly NaN / Inf) cannot reach a DMMA.
+  double* XN = smem;                                   // (dmax_pad + 4) x kLDX
+  double* XR = XN + (int64_t)(P.dmax_pad + 4) * kLDX;  // (qdmax_pad + 4) x kLDX
+  double* TH = XR + (int64_t)(P.qdmax_pad + 4) * kLDX; // Q x kTMU
   double* OUTW = TH + P.Q * kTMU;                      // kEstWarps x 3 x kTMU
   __shared__ int s_tile_ptr[kMaxEstTerms + 1];         // row tiles (8 rows) of the subdomain's terms, prefix sums
 
@@ -861,8 +871,7 @@ estimate_kernel(EstParams P, int64_t n_mu, const double* __restrict__ theta, con
     }
     d += Nk;
   }
-  const int dpad = (d + 3) & ~3;
-  for (int i = threadIdx.x; i < (dpad - d) * kTMU; i += kEstThreads) XN[(d + i / kTMU) * kLDX + (i % kTMU)] = 0.0;
+  for (int i = threadIdx.x; i < (P.dmax_pad + 4 - d) * kTMU; i += kEstThreads) XN[(d + i / kTMU) * kLDX + (i % kTMU)] = 0.0;
   __syncthreads();
   {
     int lo = 0;
@@ -876,8 +885,8 @@ estimate_kernel(EstParams P, int64_t n_mu, const double* __restrict__ theta, con
       }
       lo += Nk;
     }
-    const int qd = P.Q * d, qdpad = (qd + 3) & ~3;
-    for (int i = threadIdx.x; i < (qdpad - qd) * kTMU; i += kEstThreads) XR[(qd + i / kTMU) * kLDX + (i % kTMU)] = 0.0;
+    const int qd = P.Q * d;
+    for (int i = threadIdx.x; i < (P.qdmax_pad + 4 - qd) * kTMU; i += kEstThreads) XR[(qd + i / kTMU) * kLDX + (i % kTMU)] = 0.0;
   }
   __syncthreads();
 
@@ -1006,6 +1015,8 @@ struct OnlinePlan : lrbms_plan {
   SolveParams sp;
   SolveParamsV2 sp2;
   bool use_v2 = false;
+  bool use_band = false;        // block-banded out-of-HBM Cholesky (band.cu): systems whose factor window exceeds one SM
+  lrbms_band_plan band;
   size_t solve2_smem = 0;
   int64_t solve_stride = 0;     // doubles of factor scratch per resident CTA of the selected solve kernel
   EstParams ep;
@@ -1030,8 +1041,18 @@ int lrbms_online_plan_create(lrbms_handle_t h, const lrbms_reduced_system_t* sys
   P->ctx = h;
   P->kind = PLAN_ONLINE;
   std::string err;
-  int rc = lrbms_symbolic_build(P->sym, sys->n_sub, sys->basis_sizes, sys->n_blocks, sys->block_i, sys->block_j, &err);
+  LRBMS_REQUIRE(h, sys->solver >= LRBMS_SOLVER_AUTO && sys->solver <= LRBMS_SOLVER_BANDED, "online_plan_create: unknown solver");
+  int rc = lrbms_symbolic_basics(P->sym, sys->n_sub, sys->basis_sizes, sys->n_blocks, sys->block_i, sys->block_j, &err);
   if (rc) { delete P; return lrbms_fail(h, rc, err); }
+  // The 8x8-tile schedule is only built when a CTA-per-parameter kernel can use it: its pair lists grow like
+  // n (b / 8)^2 / 2 (135 M pairs for the 8x8x8, N = 40 system), the band solver needs none of it.
+  const double est_pairs = 0.5 * P->sym.ntc * (P->sym.half_bandwidth / 8.0 + 1.0) * (P->sym.half_bandwidth / 8.0 + 1.0);
+  bool tiles_built = sys->solver == LRBMS_SOLVER_WINDOW || sys->solver == LRBMS_SOLVER_GLOBAL_TILES ||
+               (sys->solver == LRBMS_SOLVER_AUTO && est_pairs <= 3.0e7);
+  if (tiles_built) {
+    rc = lrbms_symbolic_build(P->sym, sys->n_sub, sys->basis_sizes, sys->n_blocks, sys->block_i, sys->block_j, &err);
+    if (rc) { delete P; return lrbms_fail(h, rc, err); }
+  }
   const lrbms_symbolic& S = P->sym;
   const int Q = sys->Q, Qf = sys->Qf;
 
@@ -1046,7 +1067,9 @@ int lrbms_online_plan_create(lrbms_handle_t h, const lrbms_reduced_system_t* sys
     cudaError_t e = cudaMemcpy(hb.data(), sys->lhs_blocks, sizeof(double) * n_doubles, cudaMemcpyDeviceToHost);
     if (e != cudaSuccess) { delete P; return lrbms_fail(h, LRBMS_ERR_CUDA, cudaGetErrorString(e)); }
   }
-  std::vector<double> tiles((size_t)Q * S.n_a_tiles * 64, 0.0);
+  std::vector<double> tiles;
+  if (tiles_built) {
+  tiles.assign((size_t)Q * S.n_a_tiles * 64, 0.0);
   auto slot_of = [&](int I, int J) {
     const int32_t* b = S.row_idx.data() + S.col_ptr[J];
     const int32_t* e = S.row_idx.data() + S.col_ptr[J + 1];
@@ -1068,22 +1091,33 @@ int lrbms_online_plan_create(lrbms_handle_t h, const lrbms_reduced_system_t* sys
           if (r / 8 == cc / 8) tl[(cc & 7) * 8 + (r & 7)] = blk[(int64_t)a * Nj + c];
         }
     }
+  }
   std::vector<double> rhs_h((size_t)Qf * S.n_pad, 0.0);
+  std::vector<double> tmp((size_t)Qf * S.n_red);     // [Qf][n_red], as given
   {
-    std::vector<double> tmp((size_t)Qf * S.n_red);
     cudaError_t e = cudaMemcpy(tmp.data(), sys->rhs, sizeof(double) * tmp.size(), cudaMemcpyDeviceToHost);
     if (e != cudaSuccess) { delete P; return lrbms_fail(h, LRBMS_ERR_CUDA, cudaGetErrorString(e)); }
     for (int q = 0; q < Qf; ++q) std::copy(tmp.begin() + (size_t)q * S.n_red, tmp.begin() + (size_t)(q + 1) * S.n_red, rhs_h.begin() + (size_t)q * S.n_pad);
   }
 
-  SolveParams& sp = P->sp;
-  sp.n_red = S.n_red; sp.n_pad = S.n_pad; sp.ntc = S.ntc; sp.n_tiles = (int32_t)S.n_tiles(); sp.Q = Q; sp.Qf = Qf;
-  sp.n_theta = Q + Qf; sp.n_a_tiles = S.n_a_tiles;
-  sp.work_stride = ((int64_t)S.n_tiles() + 2 * S.ntc) * 64;
+// CUDA calls after the plan object exists: destroy it on failure (no leaked plans on error paths)
+#define PLAN_CUDA_CHECK(expr)                                                                          \
+  do {                                                                                                 \
+    cudaError_t _e = (expr);                                                                           \
+    if (_e != cudaSuccess) {                                                                           \
+      lrbms_plan_destroy(P);                                                                           \
+      return lrbms_fail(h, LRBMS_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));        \
+    }                                                                                                  \
+  } while (0)
   int32_t *d_i32 = nullptr;
   double* d_f64 = nullptr;
 #define UP_I32(field, vec) do { rc = plan_upload(P, &d_i32, vec); if (rc) { lrbms_plan_destroy(P); return rc; } field = d_i32; } while (0)
 #define UP_F64(field, vec) do { rc = plan_upload(P, &d_f64, vec); if (rc) { lrbms_plan_destroy(P); return rc; } field = d_f64; } while (0)
+  SolveParams& sp = P->sp;
+  if (tiles_built) {
+  sp.n_red = S.n_red; sp.n_pad = S.n_pad; sp.ntc = S.ntc; sp.n_tiles = (int32_t)S.n_tiles(); sp.Q = Q; sp.Qf = Qf;
+  sp.n_theta = Q + Qf; sp.n_a_tiles = S.n_a_tiles;
+  sp.work_stride = ((int64_t)S.n_tiles() + 2 * S.ntc) * 64;
   UP_I32(sp.col_ptr, S.col_ptr);
   UP_I32(sp.row_idx, S.row_idx);
   UP_I32(sp.pair_ptr, S.pair_ptr);
@@ -1094,21 +1128,18 @@ int lrbms_online_plan_create(lrbms_handle_t h, const lrbms_reduced_system_t* sys
   UP_F64(sp.rhs, rhs_h);
 
   P->solve_smem = sizeof(double) * ((size_t)S.n_pad + 64 + 64 + kSolveWarps * 8 + sp.n_theta);
-  if (P->solve_smem > (size_t)h->max_smem_optin) {
-    lrbms_plan_destroy(P);
-    return lrbms_fail(h, LRBMS_ERR_UNSUPPORTED, "online_plan_create: reduced dimension too large for the shared-memory solve vector");
-  }
-  if (P->solve_smem > 48 * 1024)
-    LRBMS_CUDA_CHECK(h, cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->solve_smem));
-  {
+  if (sys->solver == LRBMS_SOLVER_GLOBAL_TILES) {
+    if (P->solve_smem > (size_t)h->max_smem_optin) {
+      lrbms_plan_destroy(P);
+      return lrbms_fail(h, LRBMS_ERR_UNSUPPORTED, "online_plan_create: reduced dimension too large for the shared-memory solve vector");
+    }
+    if (P->solve_smem > 48 * 1024)
+      PLAN_CUDA_CHECK(cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->solve_smem));
     int per_sm = 0;
-    LRBMS_CUDA_CHECK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, solve_kernel, kSolveThreads, P->solve_smem));
+    PLAN_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, solve_kernel, kSolveThreads, P->solve_smem));
     if (per_sm < 1) per_sm = 1;
-    const char* env = getenv("LRBMS_SOLVE_CTAS_PER_SM");
-    if (env && atoi(env) > 0) per_sm = std::min(per_sm, atoi(env));
     P->solve_grid = per_sm * h->sm_count;
   }
-
   P->solve_stride = sp.work_stride;
   // ---- shared-memory-window kernel (v2): used whenever the live window of L fits into shared memory
   {
@@ -1120,8 +1151,11 @@ int lrbms_online_plan_create(lrbms_handle_t h, const lrbms_reduced_system_t* sys
                                            (size_t)kABufs * mac * Q * 64) +
                          16 * ((size_t)kMetaBufs * MT + (size_t)(S.ntc + 1) + 2 * (size_t)S.ntc) + 8 * (size_t)kMetaBufs * mcp +
                          4 * (3 * (size_t)kMetaBufs * MT + S.ca_tile.size()) + 64;
-    const char* force_v1 = getenv("LRBMS_SOLVE_V1");
-    if (bytes <= (size_t)h->max_smem_optin && !(force_v1 && atoi(force_v1) > 0)) {
+    cudaFuncAttributes fa2;
+    PLAN_CUDA_CHECK(cudaFuncGetAttributes(&fa2, solve_kernel_v2));
+    // the static shared memory of the kernel (mbarriers, status word) counts against the same per-block limit
+    if (bytes + fa2.sharedSizeBytes <= (size_t)h->max_smem_optin && sys->solver != LRBMS_SOLVER_GLOBAL_TILES &&
+        sys->solver != LRBMS_SOLVER_BANDED) {
       SolveParamsV2& s2 = P->sp2;
       s2.base = sp;
       s2.base.work_stride = (int64_t)S.n_tiles() * 64;
@@ -1141,30 +1175,47 @@ int lrbms_online_plan_create(lrbms_handle_t h, const lrbms_reduced_system_t* sys
       UP_I32(tmp, S.ccol3);  s2.ccol3 = reinterpret_cast<const int4*>(tmp);
       UP_I32(tmp, S.cdesc);  s2.cdesc = reinterpret_cast<const int4*>(tmp);
       UP_I32(tmp, S.win_ab); s2.win_ab = reinterpret_cast<const int2*>(tmp);
-      s2.timing = nullptr;
       s2.staggered = S.staggered;
-      { const char* pd = getenv("LRBMS_SOLVE_BIASED_DEAL"); s2.plain_deal = (pd && atoi(pd) > 0) ? 1 : 0; }
-      { const char* ns = getenv("LRBMS_SOLVE_NOSTORE"); s2.no_store = (ns && atoi(ns) > 0) ? 1 : 0; }
+#ifdef LRBMS_DEVTOOLS
+      s2.timing = nullptr;
       if (const char* tenv = getenv("LRBMS_SOLVE_TIMING")) {
         if (atoi(tenv) > 0) {
           rc = plan_alloc(P, &s2.timing, (size_t)kV2Warps * 8);
           if (rc) { lrbms_plan_destroy(P); return rc; }
-          cudaMemset(s2.timing, 0, sizeof(long long) * kV2Warps * 8);
+          PLAN_CUDA_CHECK(cudaMemset(s2.timing, 0, sizeof(long long) * kV2Warps * 8));
         }
       }
+#endif
       P->solve2_smem = bytes;
-      LRBMS_CUDA_CHECK(h, cudaFuncSetAttribute(solve_kernel_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+      PLAN_CUDA_CHECK(cudaFuncSetAttribute(solve_kernel_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
       P->use_v2 = true;
       P->solve_grid = h->sm_count;
       P->solve_stride = s2.base.work_stride;
     }
   }
 
+  }  // tiles_built
+  if (sys->solver == LRBMS_SOLVER_WINDOW && !P->use_v2) {
+    lrbms_plan_destroy(P);
+    return lrbms_fail(h, LRBMS_ERR_UNSUPPORTED, "online_plan_create: the live factor window does not fit the shared memory of one SM");
+  }
+  // ---- band solver (band.cu): everything the CTA-per-parameter window kernel cannot hold
+  if (!P->use_v2 && sys->solver != LRBMS_SOLVER_GLOBAL_TILES) {
+    rc = lrbms_band_build(P, P->band, S.n_sub, S.sizes.data(), S.offsets.data(), Q, Qf, sys->n_blocks, sys->block_i, sys->block_j,
+                          sys->block_offset, hb.data(), tmp.data());
+    if (rc) { lrbms_plan_destroy(P); return rc; }
+    P->use_band = true;
+    P->solve_grid = h->sm_count;
+  }
+
   // ---- estimator tables
   P->has_estimator = sys->n_terms > 0;
   if (P->has_estimator) {
-    LRBMS_REQUIRE(h, sys->nbh_ptr && sys->nbh_idx && sys->terms && sys->est_matrices && sys->rf_squared && sys->r_scale &&
-                         sys->theta_bar && sys->theta_hat, "online_plan_create: estimator data missing");
+    if (!(sys->nbh_ptr && sys->nbh_idx && sys->terms && sys->est_matrices && sys->rf_squared && sys->r_scale &&
+          sys->theta_bar && sys->theta_hat)) {
+      lrbms_plan_destroy(P);
+      return lrbms_fail(h, LRBMS_ERR_INVALID, "online_plan_create: estimator data missing");
+    }
     EstParams& ep = P->ep;
     ep.n_sub = S.n_sub; ep.n_red = S.n_red; ep.Q = Q; ep.n_theta = Q + Qf;
     std::vector<int32_t> nbh_ptr(sys->nbh_ptr, sys->nbh_ptr + S.n_sub + 1);
@@ -1223,12 +1274,11 @@ int lrbms_online_plan_create(lrbms_handle_t h, const lrbms_reduced_system_t* sys
     UP_F64(ep.rf2, rf2);
     UP_F64(ep.r_scale, rs);
     auto est_bytes = [&](int tmu) {
-      return sizeof(double) * ((size_t)(ep.dmax_pad + ep.qdmax_pad) * (tmu + 4) + (size_t)Q * tmu + kEstWarps * 3 * tmu);
+      return sizeof(double) * ((size_t)(ep.dmax_pad + ep.qdmax_pad + 8) * (tmu + 4) + (size_t)Q * tmu + kEstWarps * 3 * tmu);
     };
     // 32 parameters per CTA when two such CTAs fit one SM (the staging phase of one overlaps the DMMAs of the other:
     // 4.5 instead of 5.4 ms per 10 000 parameters at C2), else the largest tile that fits at all
     P->est_tmu = (2 * (est_bytes(32) + 1024) <= (size_t)h->max_smem_optin) ? 32 : kTMUMax;
-    if (const char* e = getenv("LRBMS_EST_TMU")) { const int v = atoi(e); if (v == 8 || v == 16 || v == 32 || v == 64) P->est_tmu = v; }
     while (P->est_tmu > 8 && est_bytes(P->est_tmu) > (size_t)h->max_smem_optin) P->est_tmu /= 2;
     P->est_smem = est_bytes(P->est_tmu);
     if (P->est_smem > (size_t)h->max_smem_optin) {
@@ -1239,7 +1289,7 @@ int lrbms_online_plan_create(lrbms_handle_t h, const lrbms_reduced_system_t* sys
       const void* fn = P->est_tmu == 64 ? (const void*)estimate_kernel<64>
                        : P->est_tmu == 32 ? (const void*)estimate_kernel<32>
                        : P->est_tmu == 16 ? (const void*)estimate_kernel<16> : (const void*)estimate_kernel<8>;
-      LRBMS_CUDA_CHECK(h, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->est_smem));
+      PLAN_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->est_smem));
     }
     CombineParams& cp = P->cp;
     cp.n_sub = S.n_sub; cp.Q = Q; cp.n_theta = Q + Qf; cp.alpha_first = sys->alpha_returns_first;
@@ -1247,13 +1297,21 @@ int lrbms_online_plan_create(lrbms_handle_t h, const lrbms_reduced_system_t* sys
   }
 #undef UP_I32
 #undef UP_F64
-  P->info_launches = 3;
+  P->info_launches = P->use_band ? 3.0 * P->band.nbc + 4 : 3;
   P->info_ctas = P->solve_grid;
+  // introspection (lrbms_plan_info 6 .. 9): which solve kernel the plan selected, executed factor flops per parameter
+  // (the 8x8-tile count for the CTA-per-parameter kernels, the dense-band count of the band solver), half bandwidth
+  P->info_solver = P->use_v2 ? LRBMS_SOLVER_WINDOW : P->use_band ? LRBMS_SOLVER_BANDED : LRBMS_SOLVER_GLOBAL_TILES;
+  P->info_solve_flops = P->use_band ? P->band.flops_per_mu : (double)S.flops;
+  P->info_half_bandwidth = S.half_bandwidth;
+  // uploads and clears above ran on the legacy default stream: finish them before a caller's non-blocking stream runs the plan
+  PLAN_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)0));
   *out = P;
   return LRBMS_OK;
 }
 
 static size_t solve_ws_bytes(const OnlinePlan* P, int64_t n_mu) {
+  if (P->use_band) return lrbms_band_workspace_bytes(P->band, n_mu);
   const int64_t ctas = std::min<int64_t>(P->solve_grid, std::max<int64_t>(1, n_mu));
   return (size_t)ctas * P->solve_stride * sizeof(double);
 }
@@ -1274,6 +1332,13 @@ int lrbms_online_solve(lrbms_plan_t plan, int64_t n_mu, const double* theta, dou
   OnlinePlan* P = static_cast<OnlinePlan*>(plan);
   LRBMS_REQUIRE(P->ctx, theta && u && workspace, "online_solve: null argument");
   if (n_mu <= 0) return LRBMS_OK;
+  if (P->use_band) {
+    // the band solver works through the batch in chunks of as many parameters as the workspace holds factors for
+    LRBMS_REQUIRE(P->ctx, lrbms_band_chunk(P->band, n_mu, workspace_bytes) >= 1,
+                  "online_solve: workspace too small (see lrbms_online_workspace_bytes)");
+    return lrbms_band_solve(P->ctx, P->band, n_mu, theta, u, info, workspace, solve_ws_bytes(P, n_mu) <= workspace_bytes
+                            ? solve_ws_bytes(P, n_mu) : workspace_bytes, (cudaStream_t)stream);
+  }
   LRBMS_REQUIRE(P->ctx, workspace_bytes >= solve_ws_bytes(P, n_mu), "online_solve: workspace too small (see lrbms_online_workspace_bytes)");
   const int grid = (int)std::min<int64_t>(P->solve_grid, n_mu);
   if (P->use_v2)
@@ -1319,10 +1384,15 @@ int lrbms_online_sweep(lrbms_plan_t plan, int64_t n_mu, const double* theta, dou
 int lrbms_online_debug_timing(lrbms_plan_t plan, int64_t* out_host, int32_t n) {
   if (!plan || plan->kind != PLAN_ONLINE || !out_host) return LRBMS_ERR_INVALID;
   OnlinePlan* P = static_cast<OnlinePlan*>(plan);
+#ifdef LRBMS_DEVTOOLS
   if (!P->use_v2 || !P->sp2.timing) return lrbms_fail(P->ctx, LRBMS_ERR_INVALID, "debug timing is off (set LRBMS_SOLVE_TIMING=1 before creating the plan)");
   const int cnt = std::min<int>(n, kV2Warps * 8);
   LRBMS_CUDA_CHECK(P->ctx, cudaMemcpy(out_host, P->sp2.timing, sizeof(long long) * cnt, cudaMemcpyDeviceToHost));
   return cnt;
+#else
+  (void)n;
+  return lrbms_fail(P->ctx, LRBMS_ERR_UNSUPPORTED, "debug timing needs a developer build of the library (-DLRBMS_DEVTOOLS)");
+#endif
 }
 
 int lrbms_eta_max(lrbms_handle_t h, int64_t n_mu, const double* eta, double* max_out, int64_t* argmax_out, void* stream) {

@@ -587,10 +587,35 @@ static void dispatch_mt(const ProjLaunch& L, const ProjectPlan* P, cudaStream_t 
   }
 }
 
+// raises the dynamic shared-memory limit of one gram_kernel instantiation; called once per launch bucket at plan creation
+template <int WM, int WN>
+static cudaError_t prepare_gram() {
+  return cudaFuncSetAttribute(gram_kernel<WM, WN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)(sizeof(double) * gram_smem_doubles<WM, WN>()));
+}
+template <int WM>
+static cudaError_t prepare_gram_n(int nt) {
+  switch (nt) {
+    case 1: return prepare_gram<WM, 1>();
+    case 2: return prepare_gram<WM, 2>();
+    case 3: return prepare_gram<WM, 3>();
+    case 4: return prepare_gram<WM, 4>();
+    default: return prepare_gram<WM, 5>();
+  }
+}
+static cudaError_t prepare_gram_mn(int mt, int nt) {
+  switch (mt) {
+    case 1: return prepare_gram_n<1>(nt);
+    case 2: return prepare_gram_n<2>(nt);
+    case 3: return prepare_gram_n<3>(nt);
+    case 4: return prepare_gram_n<4>(nt);
+    default: return prepare_gram_n<5>(nt);
+  }
+}
+
 template <int WM, int WN>
 static void launch_gram(const ProjLaunch& L, const ProjectPlan* P, cudaStream_t s) {
   const size_t smem = sizeof(double) * gram_smem_doubles<WM, WN>();
-  cudaFuncSetAttribute(gram_kernel<WM, WN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   gram_kernel<WM, WN><<<L.n_items, kGramThreads, smem, s>>>(L.d_items, P->d_descs, P->d_partials, P->d_flags, P->d_counters,
                                                         P->d_group_base);
 }
@@ -625,8 +650,16 @@ void ProjectPlan::ensure_info() {
   unsigned char* d_flag = nullptr;
   int max_cols = 1;
   for (const auto& d : host_descs) max_cols = std::max(max_cols, d.n_cols);
-  if (cudaMalloc((void**)&d_cnt, 2 * sizeof(unsigned long long)) != cudaSuccess) return;
-  if (cudaMalloc((void**)&d_flag, (size_t)max_cols) != cudaSuccess) { cudaFree(d_cnt); return; }
+  // any CUDA failure leaves the counts at NaN (never a silently wrong figure) and records the message
+  auto give_up = [&](cudaError_t e) {
+    info_bytes = info_bytes_survey = info_flops = NAN;
+    lrbms_fail(ctx, LRBMS_ERR_CUDA, std::string("plan accounting: ") + cudaGetErrorString(e));
+    if (d_cnt) cudaFree(d_cnt);
+    if (d_flag) cudaFree(d_flag);
+  };
+  cudaError_t e = cudaMalloc((void**)&d_cnt, 2 * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&d_flag, (size_t)max_cols);
+  if (e != cudaSuccess) { give_up(e); return; }
   for (const auto& d : host_descs) {
     double nl = d.NL, nr = d.NR, r = d.n_rows, c = d.n_cols;
     if (!d.rowptr) {
@@ -637,12 +670,15 @@ void ProjectPlan::ensure_info() {
     int32_t nnz = 0;
     unsigned long long cnt[2] = {0, 0};
     if (d.n_rows > 0) {
-      cudaMemcpy(&nnz, d.rowptr + d.n_rows, sizeof(int32_t), cudaMemcpyDeviceToHost);
-      cudaMemset(d_cnt, 0, 2 * sizeof(unsigned long long));
-      cudaMemset(d_flag, 0, (size_t)std::max(1, d.n_cols));
-      csr_stats_kernel<<<64, 256>>>(d.rowptr, d.colind, d.n_rows, d_flag, d_cnt);
-      count_flags_kernel<<<64, 256>>>(d_flag, d.n_cols, d_cnt);
-      cudaMemcpy(cnt, d_cnt, sizeof(cnt), cudaMemcpyDeviceToHost);
+      e = cudaMemcpy(&nnz, d.rowptr + d.n_rows, sizeof(int32_t), cudaMemcpyDeviceToHost);
+      if (e == cudaSuccess) e = cudaMemset(d_cnt, 0, 2 * sizeof(unsigned long long));
+      if (e == cudaSuccess) e = cudaMemset(d_flag, 0, (size_t)std::max(1, d.n_cols));
+      if (e == cudaSuccess) {
+        csr_stats_kernel<<<64, 256>>>(d.rowptr, d.colind, d.n_rows, d_flag, d_cnt);
+        count_flags_kernel<<<64, 256>>>(d_flag, d.n_cols, d_cnt);
+        e = cudaMemcpy(cnt, d_cnt, sizeof(cnt), cudaMemcpyDeviceToHost);
+      }
+      if (e != cudaSuccess) { give_up(e); return; }
     }
     info_bytes += 12.0 * nnz + 4.0 * (r + 1) + 8.0 * (double)cnt[1] * nr + 8.0 * (double)cnt[0] * nl + 8.0 * nl * nr;
     info_bytes_survey += 12.0 * nnz + 4.0 * (r + 1) + 8.0 * c * nr + 8.0 * r * nl + 8.0 * nl * nr;
@@ -725,6 +761,10 @@ int lrbms_spmm_plan_create(lrbms_handle_t h, int32_t n_desc, const lrbms_spmm_de
     P->info_bytes += b;
     P->info_bytes_survey += b;
     P->info_flops += 2.0 * nnz * d.N;
+  }
+  if (cudaStreamSynchronize((cudaStream_t)0) != cudaSuccess) {
+    lrbms_plan_destroy(P);
+    return lrbms_fail(h, LRBMS_ERR_CUDA, "spmm_plan_create: stream sync failed");
   }
   *out = P;
   return LRBMS_OK;
@@ -836,8 +876,9 @@ int lrbms_project_plan_create(lrbms_handle_t h, int32_t n_desc, const lrbms_proj
   if (!rc) rc = plan_alloc(P, &P->d_flags, (size_t)std::max<int64_t>(1, n_partials));
   if (!rc) rc = plan_alloc(P, &P->d_counters, (size_t)std::max(1, n_groups));
   if (!rc) {
-    cudaMemset(P->d_counters, 0, sizeof(int32_t) * std::max(1, n_groups));
-    cudaMemset(P->d_flags, 0, sizeof(int32_t) * std::max<int64_t>(1, n_partials));
+    cudaError_t e = cudaMemset(P->d_counters, 0, sizeof(int32_t) * std::max(1, n_groups));
+    if (e == cudaSuccess) e = cudaMemset(P->d_flags, 0, sizeof(int32_t) * std::max<int64_t>(1, n_partials));
+    if (e != cudaSuccess) rc = lrbms_fail(h, LRBMS_ERR_CUDA, std::string("project_plan_create: ") + cudaGetErrorString(e));
   }
   for (int mt = 1; mt <= kMaxTile && !rc; ++mt)
     for (int nt = 1; nt <= kMaxTile && !rc; ++nt)
@@ -847,6 +888,10 @@ int lrbms_project_plan_create(lrbms_handle_t h, int32_t n_desc, const lrbms_proj
         ProjLaunch L;
         L.mt = mt; L.nt = nt; L.has_a = kind == 1; L.gram = kind == 2; L.n_items = (int)bucket.size();
         rc = plan_upload(P, &L.d_items, bucket);
+        if (!rc && L.gram) {
+          const cudaError_t e = prepare_gram_mn(mt, nt);
+          if (e != cudaSuccess) rc = lrbms_fail(h, LRBMS_ERR_CUDA, std::string("gram_kernel shared-memory limit: ") + cudaGetErrorString(e));
+        }
         P->launches.push_back(L);
         P->info_launches += 1;
         P->info_ctas += L.n_items;
@@ -869,6 +914,8 @@ int lrbms_project_plan_create(lrbms_handle_t h, int32_t n_desc, const lrbms_proj
   std::stable_sort(P->launches.begin(), P->launches.end(), [](const ProjLaunch& a, const ProjLaunch& b) {
     return (int64_t)a.n_items * a.mt * a.nt * (a.gram ? 4 : 1) > (int64_t)b.n_items * b.mt * b.nt * (b.gram ? 4 : 1);
   });
+  // uploads and clears ran on the legacy default stream: finish them before a caller's non-blocking stream runs the plan
+  if (!rc && cudaStreamSynchronize((cudaStream_t)0) != cudaSuccess) rc = lrbms_fail(h, LRBMS_ERR_CUDA, "project_plan_create: stream sync failed");
   if (rc) { lrbms_plan_destroy(P); return rc; }
   *out = P;
   return LRBMS_OK;

@@ -15,8 +15,8 @@
 
 #include "../../include/lrbms_sm100.h"
 
-int lrbms_symbolic_build(lrbms_symbolic& S, int32_t n_sub, const int32_t* sizes, int32_t n_blocks, const int32_t* bi,
-                         const int32_t* bj, std::string* err) {
+int lrbms_symbolic_basics(lrbms_symbolic& S, int32_t n_sub, const int32_t* sizes, int32_t n_blocks, const int32_t* bi,
+                          const int32_t* bj, std::string* err) {
   auto fail = [&](const char* m) { if (err) *err = m; return (int)LRBMS_ERR_INVALID; };
   if (n_sub <= 0 || !sizes || n_blocks < 0 || (n_blocks && (!bi || !bj))) return fail("symbolic: bad arguments");
   S.n_sub = n_sub;
@@ -32,23 +32,35 @@ int lrbms_symbolic_build(lrbms_symbolic& S, int32_t n_sub, const int32_t* sizes,
   S.ntc = S.n_pad / 8;
   S.block_i.assign(bi, bi + n_blocks);
   S.block_j.assign(bj, bj + n_blocks);
-
-  // ---- tile pattern of the lower triangle of A
-  std::vector<std::vector<int32_t>> cols(S.ntc);   // cols[J] = tile rows I >= J with A_IJ != 0
   std::vector<char> has_diag(n_sub, 0);
+  S.half_bandwidth = 0;
   for (int b = 0; b < n_blocks; ++b) {
     const int i = bi[b], j = bj[b];
     if (i < 0 || i >= n_sub || j < 0 || j >= n_sub) return fail("symbolic: block index out of range");
-    if (i < j) continue;   // symmetric operator: the upper blocks are transposes of the lower ones
     if (i == j) has_diag[i] = 1;
+    if (i >= j && sizes[i] > 0 && sizes[j] > 0) S.half_bandwidth = std::max(S.half_bandwidth, S.offsets[i + 1] - 1 - S.offsets[j]);
+  }
+  for (int i = 0; i < n_sub; ++i)
+    if (sizes[i] > 0 && !has_diag[i]) return fail("symbolic: every subdomain needs its diagonal block");
+  return 0;
+}
+
+int lrbms_symbolic_build(lrbms_symbolic& S, int32_t n_sub, const int32_t* sizes, int32_t n_blocks, const int32_t* bi,
+                         const int32_t* bj, std::string* err) {
+  auto fail = [&](const char* m) { if (err) *err = m; return (int)LRBMS_ERR_INVALID; };
+  if (int rc = lrbms_symbolic_basics(S, n_sub, sizes, n_blocks, bi, bj, err)) return rc;
+
+  // ---- tile pattern of the lower triangle of A
+  std::vector<std::vector<int32_t>> cols(S.ntc);   // cols[J] = tile rows I >= J with A_IJ != 0
+  for (int b = 0; b < n_blocks; ++b) {
+    const int i = bi[b], j = bj[b];
+    if (i < j) continue;   // symmetric operator: the upper blocks are transposes of the lower ones
     if (sizes[i] == 0 || sizes[j] == 0) continue;
     const int I0 = S.offsets[i] / 8, I1 = (S.offsets[i + 1] - 1) / 8;
     const int J0 = S.offsets[j] / 8, J1 = (S.offsets[j + 1] - 1) / 8;
     for (int J = J0; J <= J1; ++J)
       for (int I = std::max(I0, J); I <= I1; ++I) cols[J].push_back(I);
   }
-  for (int i = 0; i < n_sub; ++i)
-    if (sizes[i] > 0 && !has_diag[i]) return fail("symbolic: every subdomain needs its diagonal block");
   for (int J = 0; J < S.ntc; ++J) {
     cols[J].push_back(J);
     std::sort(cols[J].begin(), cols[J].end());

@@ -10,6 +10,7 @@ struct lrbms_symbolic {
   int32_t n_red = 0;                     // sum N_i
   int32_t n_pad = 0;                     // n_red rounded up to a multiple of 8
   int32_t ntc = 0;                       // tile columns
+  int32_t half_bandwidth = 0;            // scalar half bandwidth of the stored lower blocks (max row - column)
   // L tile pattern, compressed by tile column; rows ascending, the diagonal tile first
   std::vector<int32_t> col_ptr, row_idx;
   // update pairs per target: targets are the L tiles (slot order) followed by one rhs target per tile column.
@@ -57,5 +58,8 @@ struct lrbms_symbolic {
   int64_t n_pairs() const { return (int64_t)pair_a.size(); }
 };
 
+// sizes, offsets, validation and the half bandwidth only (what the band solver needs); lrbms_symbolic_build starts with it
+int lrbms_symbolic_basics(lrbms_symbolic& S, int32_t n_sub, const int32_t* sizes, int32_t n_blocks, const int32_t* bi,
+                          const int32_t* bj, std::string* err);
 int lrbms_symbolic_build(lrbms_symbolic& S, int32_t n_sub, const int32_t* sizes, int32_t n_blocks, const int32_t* bi,
                          const int32_t* bj, std::string* err);

@@ -90,8 +90,14 @@ class BlockSwipdgDiscretization:
         for q in range(1, len(mats)):
             A = A + theta[q] * mats[q]
         opts = dict(inverse_options or {})
-        x, iters, relres = pcg_solve(DeviceCsr(A.tocsr()), f, rtol=float(opts.get('rtol', 1e-12)), max_iter=opts.get('maxiter'))
+        rtol = float(opts.get('rtol', 1e-12))
+        x, iters, relres = pcg_solve(DeviceCsr(A.tocsr()), f, rtol=rtol, max_iter=opts.get('maxiter'))
         self.last_local_correction_info = {'iterations': iters, 'relative_residual': relres, 'size': int(A.shape[0])}
+        if not relres <= rtol:
+            # the reference's apply_inverse raises on solver failure; an unconverged corrector must not enter a basis
+            from ._lib import LrbmsError
+            raise LrbmsError('local corrector solve on subdomain {} did not converge: relative residual {:.3e} > {:.1e} after '
+                             '{} iterations'.format(subdomain, relres, rtol, iters))
         sizes = [self.solution_space.subspaces[k].dim for k in nb]
         start = int(np.sum(sizes[:nb.index(subdomain)]))
         local = x[start:start + sizes[nb.index(subdomain)]]

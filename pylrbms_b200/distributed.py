@@ -3,7 +3,7 @@ in the CPU tests).  The path shards without any data-path collective (SURVEY.md 
 
 * offline -- contiguous strips of subdomains per rank (the reference's own decomposition, ``subdomains_on_rank``,
   ``estimators.py:40,70``); the reduced blocks of every rank are disjoint, so the exchange is an all-gather
-  (one broadcast per rank region), replacing the dead ``Allreduce(SUM)`` of zero-padded blocks at ``reductor.py:93``;
+  (one in-place ``all_gather_into_tensor`` over equal-stride rank regions), replacing the dead ``Allreduce(SUM)`` of zero-padded blocks at ``reductor.py:93``;
 * online -- the parameter batch is split evenly; the only exchange per sweep is the estimator maximum and its
   arg-max (replacing ``mpi_norm``'s sum-reduce, ``estimators.py:100-101``, which disappears because every rank holds
   all subdomains of the small reduced model).
@@ -44,10 +44,13 @@ def subdomains_on_rank(num_subdomains, rank, world):
 def region_layout(pending, world):
     """``pending``: list of ``(owner_rank, size)`` output requests in planning order.  Returns ``(offsets, starts)``:
     the offset of every request inside one buffer in which each rank's outputs form one contiguous region, and
-    the ``world + 1`` region boundaries."""
+    the ``world + 1`` region boundaries.  With more than one rank all regions get the same length (the largest, rounded up
+    to 32 doubles) so that the exchange is ONE in-place all-gather instead of one broadcast per rank."""
     region = np.zeros(world, dtype=np.int64)
     for r, size in pending:
         region[r] += size
+    if world > 1:
+        region[:] = (int(region.max()) + 31) // 32 * 32
     starts = np.concatenate([[0], np.cumsum(region)]).astype(np.int64)
     cursor = starts[:-1].copy()
     offsets = np.zeros(len(pending), dtype=np.int64)
@@ -58,12 +61,27 @@ def region_layout(pending, world):
 
 
 def exchange_regions(buffer, starts):
-    """All-gather of disjoint contiguous regions of ``buffer`` (rank ``r`` owns ``buffer[starts[r]:starts[r+1]]``)."""
+    """All-gather of disjoint contiguous regions of ``buffer`` (rank ``r`` owns ``buffer[starts[r]:starts[r+1]]``).
+
+    Equal-length regions (what ``region_layout`` produces): one in-place ``all_gather_into_tensor`` -- a single NCCL
+    collective over NVLink / NVSwitch, launch-latency-bound at these sizes (tens of MB), where eight serialised
+    broadcasts cost eight launches.  Unequal regions (foreign layouts) fall back to one broadcast per rank."""
     if not is_distributed():
         return
     dist = _dist()
+    world, rank = dist.get_world_size(), dist.get_rank()
+    sizes = [int(starts[r + 1]) - int(starts[r]) for r in range(world)]
+    if len(set(sizes)) == 1 and sizes[0] > 0 and int(starts[world]) == buffer.numel():
+        mine = buffer[int(starts[rank]):int(starts[rank + 1])]
+        try:
+            dist.all_gather_into_tensor(buffer, mine)
+            return
+        except (RuntimeError, NotImplementedError):     # a backend without the flat all-gather (older gloo)
+            parts = [buffer[int(starts[r]):int(starts[r + 1])] for r in range(world)]
+            dist.all_gather(parts, mine.clone())
+            return
     works = []
-    for r in range(dist.get_world_size()):
+    for r in range(world):
         a, b = int(starts[r]), int(starts[r + 1])
         if b > a:
             works.append(dist.broadcast(buffer[a:b], src=r, async_op=True))

@@ -133,6 +133,8 @@ class ReducedBlockOperator:
 
     def apply_inverse(self, V, mu=None):
         """Solve with this (assembled, symmetric positive definite) reduced operator: a one-term online plan."""
+        if hasattr(V, '__len__') and len(V) != 1:
+            raise NotImplementedError('apply_inverse: exactly one right-hand side vector (got {})'.format(len(V)))
         model = ReducedModel(_SingleTerm(self), _SingleTerm(_HostFunctional(V)), block_dims=self.source_dims)
         return model.solve(None)
 
@@ -223,6 +225,7 @@ class ReducedModel:
         self._plan_has_estimator = False
         self._work = {}
         self.linear = True
+        self.solver = 'auto'        # 'auto' | 'window' | 'banded' | 'global_tiles' (lrbms_sm100.h LRBMS_SOLVER_*)
 
     def with_(self, **kw):
         new = copy.copy(self)
@@ -338,6 +341,8 @@ class ReducedModel:
         sysc.n_sub, sysc.basis_sizes, sysc.Q, sysc.Qf = S, sizes.ctypes.data, Q, Qf
         sysc.n_blocks, sysc.block_i, sysc.block_j, sysc.block_offset = len(pattern), bi.ctypes.data, bj.ctypes.data, boff.ctypes.data
         sysc.lhs_blocks, sysc.rhs = buf.data_ptr(), rhs.data_ptr()
+        sysc.solver = {'auto': L.SOLVER_AUTO, 'window': L.SOLVER_WINDOW, 'global_tiles': L.SOLVER_GLOBAL_TILES,
+                       'banded': L.SOLVER_BANDED}[self.solver]
         keep = [bi, bj, boff, sizes, rhs, buf]
         has_est = self.estimator is not None and all('nc_{}'.format(s) in self.operators for s in self.estimator.subdomains)
         if has_est:
@@ -372,6 +377,26 @@ class ReducedModel:
         if self._plan is None:
             self._build_plan()
         return self._plan
+
+    def set_solver(self, solver):
+        """Select the solve kernel of the online plan ('auto', 'window', 'banded', 'global_tiles'); drops a built plan."""
+        if solver != self.solver:
+            self.solver, self._plan, self._work = solver, None, {}
+        return self
+
+    @property
+    def solve_kernel_name(self):
+        """Name of the solve kernel the plan selected (from the library, not from configuration)."""
+        return _lib.SOLVER_NAMES[int(self.online_plan.info(6))]
+
+    @property
+    def solve_flops_executed(self):
+        """Factorisation flops per parameter the selected kernel executes."""
+        return self.online_plan.info(7)
+
+    @property
+    def half_bandwidth(self):
+        return int(self.online_plan.info(8))
 
     def _workspace(self, n_mu):
         torch = _torch()
@@ -528,6 +553,40 @@ class ReducedModel:
         copy_stream.synchronize()                    # ... and the copies
         main.wait_stream(copy_stream)
         return bad
+
+    def sweep_eta_into(self, mus, eta_host, chunk=None):
+        """End-to-end sweep for callers that want the estimator only (parameter-space searches, greedy training: the
+        maximiser is then solved once more on its own): host parameters -> H2D -> solve + estimate chunk by chunk ->
+        D2H of ``eta`` ``(n_mu,)``.  The reduced solutions stay in one chunk-sized device buffer and never cross PCIe
+        (8 n_red bytes per parameter in ``sweep_into`` -- 102 MB per 10 000 parameters at n_red = 1 280).
+        Returns ``(bad, eta_max, argmax)``: the number of parameters flagged as not positive definite, the largest
+        ``eta`` and its index."""
+        torch = _torch()
+        th = self.thetas(mus)
+        n_mu = th.shape[0]
+        grid = max(1, self.online_plan.handle.sm_count)
+        if chunk is None:
+            chunk = min(n_mu, 128 * grid)
+        key = ('eta_only', n_mu, chunk)
+        bufs = self._work.get(key)
+        if bufs is None:
+            bufs = (torch.empty(th.shape, dtype=torch.float64).pin_memory(),
+                    torch.empty(th.shape, dtype=torch.float64, device='cuda'),
+                    torch.empty((chunk, self.n_red), dtype=torch.float64, device='cuda'),
+                    torch.empty(n_mu, dtype=torch.float64, device='cuda'),
+                    torch.empty(n_mu, dtype=torch.int32, device='cuda'))
+            self._work = {k: v for k, v in self._work.items() if not (isinstance(k, tuple) and k[0] == 'eta_only')}
+            self._work[key] = bufs
+        th_pin, th_dev, u, eta, info = bufs
+        th_pin.copy_(torch.from_numpy(th))
+        th_dev.copy_(th_pin, non_blocking=True)
+        for lo in range(0, n_mu, chunk):
+            hi = min(n_mu, lo + chunk)
+            self.sweep_device(th_dev[lo:hi], u[:hi - lo], eta[lo:hi], info=info[lo:hi])
+        mx, am = self.eta_max_device(eta)
+        eta_host.copy_(eta, non_blocking=True)
+        bad = int((info != 0).sum().item())          # synchronises the stream (the copy of eta is ordered before it)
+        return bad, float(mx.item()), int(am.item())
 
     def sweep_sharded(self, mus):
         """Multi-GPU online sweep: every rank solves + estimates its slice of ``mus`` and the ranks

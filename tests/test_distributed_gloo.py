@@ -34,9 +34,16 @@ def _worker(rank, world, port, result_dir):
         for s in range(S):
             if owner_rank(s, S, world) == rank:
                 buf[offsets[s]:offsets[s] + sizes[s]] = float(s + 1)
+        assert len({int(starts[r + 1] - starts[r]) for r in range(world)}) == 1      # equal strides: one all-gather
         exchange_regions(buf, starts)
         for s in range(S):
             assert torch.all(buf[offsets[s]:offsets[s] + sizes[s]] == float(s + 1))
+        # foreign layout with unequal regions: the broadcast path
+        starts2 = np.array([0, 5, 12])
+        buf2 = torch.zeros(12, dtype=torch.float64)
+        buf2[int(starts2[rank]):int(starts2[rank + 1])] = float(rank + 1)
+        exchange_regions(buf2, starts2)
+        assert torch.all(buf2[:5] == 1.0) and torch.all(buf2[5:] == 2.0)
         # ---- online: eta over a global batch, sharded; max and arg-max must not depend on the sharding
         n_mu = 101
         eta_global = np.cos(np.arange(n_mu) * 0.37) ** 2

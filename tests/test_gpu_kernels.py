@@ -321,7 +321,7 @@ def _random_reduced_system(rng, sx, sy, sizes, Q=2, Qf=1, couplings=None):
     return dict(S=S, sizes=sizes, off=off, n=n, nbh=nbh, blocks=blocks, dense=dense, rhs=rhs, Q=Q, Qf=Qf)
 
 
-def _make_online_plan(handle, sysd, terms_spec=None, rng=None, alpha_first=1):
+def _make_online_plan(handle, sysd, terms_spec=None, rng=None, alpha_first=1, solver=0):
     from pylrbms_b200 import _lib as L
     torch = _torch()
     S, sizes, off, blocks, Q, Qf = sysd['S'], sysd['sizes'], sysd['off'], sysd['blocks'], sysd['Q'], sysd['Qf']
@@ -344,6 +344,7 @@ def _make_online_plan(handle, sysd, terms_spec=None, rng=None, alpha_first=1):
     sysc.block_i = bi.ctypes.data; sysc.block_j = bj.ctypes.data; sysc.block_offset = offsets.ctypes.data
     sysc.lhs_blocks = d_blocks.data_ptr(); sysc.rhs = d_rhs.data_ptr()
     sysc.nbh_ptr = nbh_ptr.ctypes.data; sysc.nbh_idx = nbh_idx.ctypes.data
+    sysc.solver = solver
     est = None
     if terms_spec is not None:
         mats, terms, moff = [], [], 0
@@ -405,16 +406,17 @@ def _run_sweep(handle, plan, sysd, theta, with_est):
     (4, 4, [20] * 16),
     (8, 8, [20] * 64),                               # C2 reduced-system shape
 ])
-@pytest.mark.parametrize('force_v1', [False, True])
-def test_online_solve_matches_dense(handle, sx, sy, sizes, force_v1, monkeypatch):
-    """Both solve kernels: v2 (shared-memory window, the default when the window fits) and v1 (global scratch)."""
-    if force_v1:
-        monkeypatch.setenv('LRBMS_SOLVE_V1', '1')
-    else:
-        monkeypatch.delenv('LRBMS_SOLVE_V1', raising=False)
+@pytest.mark.parametrize('solver', [1, 2, 3])
+def test_online_solve_matches_dense(handle, sx, sy, sizes, solver):
+    """All three solve kernels (lrbms_sm100.h LRBMS_SOLVER_*): 1 the shared-memory window kernel (what AUTO picks when the
+    window fits), 2 the first-generation global-scratch tile kernel, 3 the block-banded out-of-HBM Cholesky (what AUTO picks
+    for large systems)."""
     rng = np.random.default_rng(10 + sx * 7 + sy)
     sysd = _random_reduced_system(rng, sx, sy, sizes)
-    plan, _ = _make_online_plan(handle, sysd)
+    plan, _ = _make_online_plan(handle, sysd, solver=solver)
+    out = C.c_double()
+    handle.check(handle.lib.lrbms_plan_info(plan.p, 6, C.byref(out)))
+    assert int(out.value) == solver
     n_mu = 37 if sysd['n'] < 500 else 700      # more parameters than resident CTAs for the big case
     theta = np.column_stack([np.ones(n_mu), rng.uniform(0.1, 1.0, n_mu), rng.uniform(0.5, 2.0, n_mu)])
     u, info = _run_sweep(handle, plan, sysd, theta, with_est=False)
@@ -429,11 +431,72 @@ def test_online_solve_matches_dense(handle, sx, sy, sizes, force_v1, monkeypatch
         assert np.linalg.norm(A @ u[m] - f) <= RTOL * np.linalg.norm(f) * np.linalg.cond(A) ** 0.5
 
 
-def test_online_solve_is_bit_reproducible(handle, monkeypatch):
+def _grid3d_couplings(nx, ny, nz):
+    idx = lambda x, y, z: (z * ny + y) * nx + x
+    out = []
+    for z in range(nz):
+        for y in range(ny):
+            for x in range(nx):
+                if x + 1 < nx: out.append((idx(x + 1, y, z), idx(x, y, z)))
+                if y + 1 < ny: out.append((idx(x, y + 1, z), idx(x, y, z)))
+                if z + 1 < nz: out.append((idx(x, y, z + 1), idx(x, y, z)))
+    return out
+
+
+@pytest.mark.parametrize('shape,N,n_mu', [
+    ((16, 16), 20, 300),          # BASELINE configs[2] reduced-system shape: n_red = 5 120, half bandwidth 339
+    ((4, 4, 4), 40, 24),          # configs[3] structure (six face neighbours, N = 40) at 4x4x4: n_red = 2 560, half bandwidth 679
+    ((5, 3, 2), [33, 40, 17, 64, 1, 40, 25, 40, 40, 9, 40, 40, 31, 40, 40] * 2, 11),   # ragged sizes, not multiples of 64
+])
+def test_band_solver_large_systems(handle, shape, N, n_mu):
+    """The block-banded out-of-HBM Cholesky: AUTO must select it when the factor window exceeds one SM's shared memory, and
+    it must reproduce the dense solve in the energy norm (1e-10) with a clean residual; chunked runs (workspace for fewer
+    parameters than the batch) must give bit-identical results."""
+    torch = _torch()
+    from pylrbms_b200._lib import ptr, current_stream_ptr
+    rng = np.random.default_rng(5 + len(shape) + shape[0])
+    S = int(np.prod(shape))
+    sizes = [N] * S if np.isscalar(N) else list(N)
+    if len(shape) == 2:
+        sysd = _random_reduced_system(rng, shape[0], shape[1], sizes)
+    else:
+        sysd = _random_reduced_system(rng, S, 1, sizes, couplings=_grid3d_couplings(*shape))
+    plan, _ = _make_online_plan(handle, sysd)            # AUTO
+    out = C.c_double()
+    handle.check(handle.lib.lrbms_plan_info(plan.p, 6, C.byref(out)))
+    assert int(out.value) == 3, 'AUTO did not select the band solver'
+    theta = np.column_stack([np.ones(n_mu), rng.uniform(0.1, 1.0, n_mu), rng.uniform(0.5, 2.0, n_mu)])
+    u, info = _run_sweep(handle, plan, sysd, theta, with_est=False)
+    assert np.all(info == 0)
+    for m in np.linspace(0, n_mu - 1, 3).astype(int):
+        A = theta[m, 0] * sysd['dense'][0] + theta[m, 1] * sysd['dense'][1]
+        f = theta[m, 2] * sysd['rhs'][0]
+        ref = np.linalg.solve(A, f)
+        e = u[m] - ref
+        assert np.sqrt(e @ A @ e) <= RTOL * np.sqrt(ref @ A @ ref), 'mu {}'.format(m)
+        assert np.linalg.norm(A @ u[m] - f) <= RTOL * np.linalg.norm(f) * np.linalg.cond(A) ** 0.5
+    # chunked: a workspace that holds the factors of 5 parameters only
+    ws = C.c_size_t()
+    handle.check(handle.lib.lrbms_online_workspace_bytes(plan.p, 5, C.byref(ws)))
+    d_theta = dev(theta)
+    u2 = torch.zeros((n_mu, sysd['n']), dtype=torch.float64, device='cuda')
+    info2 = torch.ones(n_mu, dtype=torch.int32, device='cuda')
+    work = torch.empty(ws.value, dtype=torch.uint8, device='cuda')
+    handle.check(handle.lib.lrbms_online_solve(plan.p, n_mu, ptr(d_theta), ptr(u2), ptr(info2), ptr(work), ws.value,
+                                               current_stream_ptr()))
+    torch.cuda.synchronize()
+    assert np.array_equal(u2.cpu().numpy(), u) and int(info2.abs().sum().item()) == 0
+    # not positive definite: reported per parameter, the others unaffected
+    theta_bad = theta[:4].copy()
+    theta_bad[2, :2] = [-1.0, -1.0]
+    ub, infob = _run_sweep(handle, plan, sysd, theta_bad, with_est=False)
+    assert infob[2] > 0 and np.all(infob[[0, 1, 3]] == 0) and np.array_equal(ub[[0, 1, 3]], u[[0, 1, 3]])
+
+
+def test_online_solve_is_bit_reproducible(handle):
     """The column pipeline of solve_kernel_v2 lets the two halves of its update warps run the triangular solve and the pair
     loop in opposite order with a single barrier per tile column; a data race there would show as run-to-run differences.
     Same parameters in a different order and batch size must give bit-identical solutions."""
-    monkeypatch.delenv('LRBMS_SOLVE_V1', raising=False)
     rng = np.random.default_rng(77)
     sysd = _random_reduced_system(rng, 8, 8, [20] * 64)              # C2 reduced-system shape
     plan, _ = _make_online_plan(handle, sysd)
@@ -453,11 +516,10 @@ def test_online_solve_is_bit_reproducible(handle, monkeypatch):
         assert np.sqrt(e @ A @ e) <= RTOL * np.sqrt(ref @ A @ ref), 'mu {}'.format(m)
 
 
-def test_online_solve_barrier_schedule(handle, monkeypatch):
+def test_online_solve_barrier_schedule(handle):
     """A sparsity pattern in which a target has a pair with source column J - 2 but no carrier tile in column J - 1: the
     symbolic phase must pick the barrier schedule of solve_kernel_v2 and the kernel must still reproduce the dense solve."""
     from pylrbms_b200._lib import Symbolic
-    monkeypatch.delenv('LRBMS_SOLVE_V1', raising=False)
     rng = np.random.default_rng(21)
     # subdomains 2 and 3 couple to 0 (fill in (3, 2) from source 0); subdomain 1 is isolated: no tile (3, 1) or (2, 1)
     couplings = [(2, 0), (3, 0), (5, 4), (6, 4), (6, 2)]
@@ -520,6 +582,7 @@ def _estimate_reference(sysd, est, theta, u, alpha_first=True):
 ])
 def test_online_sweep_estimator_matches_numpy(handle, sx, sy, sizes, alpha_first):
     from pylrbms_b200 import _lib as L
+    from pylrbms_b200._lib import current_stream_ptr as _cs
     rng = np.random.default_rng(20 + sx)
     sysd = _random_reduced_system(rng, sx, sy, sizes)
     spec = [  # the term set of reference estimators.py:71-85 (shapes as in SURVEY.md section 8a a7-a9)
@@ -534,7 +597,11 @@ def test_online_sweep_estimator_matches_numpy(handle, sx, sy, sizes, alpha_first
     plan, est = _make_online_plan(handle, sysd, spec, rng, alpha_first=alpha_first)
     n_mu = 45                       # not a multiple of the 32-parameter tile
     theta = np.column_stack([np.ones(n_mu), rng.uniform(0.1, 1.0, n_mu), np.ones(n_mu)])
+    # every SM's shared memory holds NaNs before the sweep: rows of the staged neighbourhood vectors that a term reads
+    # beyond its own extent (unaligned slices, neighbourhoods smaller than the largest) must have been zero-filled
+    handle.check(handle.lib.lrbms_debug_poison_shared(handle.h, _cs()))
     u, info, eta, parts, ind = _run_sweep(handle, plan, sysd, theta, with_est=True)
+    assert np.all(np.isfinite(eta)) and np.all(np.isfinite(parts))
     assert np.all(info == 0)
     rparts, reta, rind = _estimate_reference(sysd, est, theta, u, alpha_first=bool(alpha_first))
     for kind in range(3):

@@ -127,7 +127,9 @@ def test_solve_and_estimate_match_oracle(handle, num_subdomains, cells, basis_si
     for k, mu in enumerate(mus):
         U_ref = rd_ref.solve(mu)
         eta_ref, parts_ref, ind_ref = rd_ref.estimate(U_ref, mu, decompose=True)
-        assert np.abs(U_b.data[k] - U_ref.data[0]).max() <= 1e-9 * np.abs(U_ref.data).max()
+        A = rd_ref.operator.assemble(rd_ref.parse_parameter(mu)).matrix
+        e = U_b.data[k] - U_ref.data[0]
+        assert np.sqrt(e @ A @ e) <= RTOL * np.sqrt(U_ref.data[0] @ A @ U_ref.data[0])       # energy norm, 1e-10
         assert abs(eta_b[k] - eta_ref) <= RTOL * abs(eta_ref)
         assert np.abs(ind_b[:, k] - ind_ref[:, 0]).max() <= 10 * RTOL * np.abs(ind_ref).max()
     # estimate_batch on given solutions
@@ -244,7 +246,9 @@ def test_empty_local_bases(handle):
     for k, mu in enumerate(mus):
         U_ref = rd_ref.solve(mu)
         eta_ref, parts_ref, _ = rd_ref.estimate(U_ref, mu, decompose=True)
-        assert np.abs(U.data[k] - U_ref.data[0]).max() <= 1e-9 * np.abs(U_ref.data).max()
+        A = rd_ref.operator.assemble(rd_ref.parse_parameter(mu)).matrix
+        e = U.data[k] - U_ref.data[0]
+        assert np.sqrt(e @ A @ e) <= RTOL * np.sqrt(U_ref.data[0] @ A @ U_ref.data[0])
         assert abs(eta[k] - eta_ref) <= RTOL * abs(eta_ref)
         assert np.abs(parts[0][:, k] - parts_ref[0][:, 0]).max() <= RTOL * max(np.abs(parts_ref[0]).max(), 1e-300)
 
@@ -323,5 +327,8 @@ def test_incremental_reprojection_matches_full(handle, num_subdomains, cells, ba
         mus = np.linspace(data.parameter_range[0], data.parameter_range[1], 4)
         U, eta, _, _ = rd.sweep(mus, decompose=True)
         U2, eta2, _, _ = rd_full.sweep(mus, decompose=True)
-        assert np.abs(U.data - U2.data).max() <= 1e-9 * np.abs(U2.data).max()
-        assert np.abs(eta - eta2).max() <= 1e-9 * np.abs(eta2).max()
+        for k, mu in enumerate(mus):
+            A = sum(c * o.to_dense() for c, o in zip(rd_full.thetas([mu])[0], rd_full.operator.operators))
+            e = U.data[k] - U2.data[k]
+            assert np.sqrt(e @ A @ e) <= RTOL * np.sqrt(U2.data[k] @ A @ U2.data[k])
+        assert np.abs(eta - eta2).max() <= RTOL * np.abs(eta2).max()

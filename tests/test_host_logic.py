@@ -53,7 +53,10 @@ def test_sharding_arithmetic():
         assert max(b - a for a, b in cuts) - min(b - a for a, b in cuts) <= 1
     pending = [(0, 4), (1, 3), (0, 2), (2, 5), (1, 1)]
     offsets, starts = region_layout(pending, 3)
-    assert list(starts) == [0, 6, 10, 15] and list(offsets) == [0, 6, 4, 10, 9]
+    # equal strides (largest region, 6 doubles, rounded up to 32) so that the exchange is one in-place all-gather
+    assert list(starts) == [0, 32, 64, 96] and list(offsets) == [0, 32, 4, 64, 35]
+    offsets1, starts1 = region_layout(pending, 1) if False else region_layout([(0, 4), (0, 3)], 1)
+    assert list(starts1) == [0, 7] and list(offsets1) == [0, 4]                    # single rank: tight packing
 
 
 def test_fixture_structure_matches_appendix_b():
@@ -84,7 +87,11 @@ def test_fixture_structure_matches_appendix_b():
 def test_bench_flop_model_matches_survey():
     sys.path.insert(0, ROOT)
     import bench
-    fl = bench.survey_flops_per_mu(8, 20, 2)
+    nbh = []
+    for s_ in range(64):
+        ix, iy = s_ % 8, s_ // 8
+        nbh.append(sorted([s_] + [s_ - 8] * (iy > 0) + [s_ - 1] * (ix > 0) + [s_ + 1] * (ix < 7) + [s_ + 8] * (iy < 7)))
+    fl = bench.survey_flops_model([20] * 64, nbh, 2, 179)
     assert fl['n_red'] == 1280 and fl['blocks'] == 288 and fl['half_bandwidth'] == 180
     assert abs(fl['solve'] - (0.46e6 + 41.5e6 + 0.92e6)) < 0.1e6
 
