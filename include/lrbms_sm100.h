@@ -135,6 +135,14 @@ typedef struct {
 
 int lrbms_project_plan_create(lrbms_handle_t h, int32_t n_desc, const lrbms_project_desc_t* descs_host,
                               lrbms_plan_t* out);
+/* The same with caller-provided scratch ("the library allocates nothing except an explicitly sized
+ * workspace handed in by the caller").  Descriptors too wide for the fused kernel (NL or NR > 40 with a sparse operator) are
+ * computed as W = A VR into scratch followed by a dense Gram; lrbms_project_plan_scratch_bytes says how much scratch a
+ * descriptor list needs, lrbms_project_plan_create_ws carves the W arrays out of `scratch` (device, 256-byte aligned, must
+ * outlive the plan; plans that never run concurrently may share it) instead of allocating them. */
+int lrbms_project_plan_scratch_bytes(int32_t n_desc, const lrbms_project_desc_t* descs_host, size_t* bytes);
+int lrbms_project_plan_create_ws(lrbms_handle_t h, int32_t n_desc, const lrbms_project_desc_t* descs_host, void* scratch,
+                                 size_t scratch_bytes, lrbms_plan_t* out);
 
 /* Incremental re-projection after an enrichment.  The reference re-runs the whole        */
 /* reductor.reduce() after every enrichment (online_enrichment.py:49-51); only the rows / columns that belong to the      */

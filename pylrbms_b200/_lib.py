@@ -18,7 +18,8 @@ EXPORTS = [
     'lrbms_version', 'lrbms_create', 'lrbms_destroy', 'lrbms_last_error', 'lrbms_device_sm_count', 'lrbms_set_option', 'lrbms_debug_poison_shared',
     'lrbms_va_scal', 'lrbms_va_axpy', 'lrbms_va_pairwise_dot', 'lrbms_va_lincomb', 'lrbms_va_copy_cols',
     'lrbms_va_transpose_in', 'lrbms_va_transpose_out',
-    'lrbms_spmm_plan_create', 'lrbms_project_plan_create', 'lrbms_plan_run', 'lrbms_plan_destroy', 'lrbms_plan_info',
+    'lrbms_spmm_plan_create', 'lrbms_project_plan_create', 'lrbms_project_plan_scratch_bytes',
+    'lrbms_project_plan_create_ws', 'lrbms_plan_run', 'lrbms_plan_destroy', 'lrbms_plan_info',
     'lrbms_symbolic_create', 'lrbms_symbolic_destroy', 'lrbms_symbolic_info', 'lrbms_symbolic_get',
     'lrbms_online_plan_create', 'lrbms_online_workspace_bytes', 'lrbms_online_solve', 'lrbms_online_estimate',
     'lrbms_online_sweep', 'lrbms_eta_max', 'lrbms_online_debug_timing',
@@ -106,6 +107,8 @@ def load_library():
             'lrbms_va_transpose_out': (C.c_int, [vp, i64, i32, vp, i32, vp, vp]),
             'lrbms_spmm_plan_create': (C.c_int, [vp, i32, vp, P(vp)]),
             'lrbms_project_plan_create': (C.c_int, [vp, i32, vp, P(vp)]),
+            'lrbms_project_plan_scratch_bytes': (C.c_int, [i32, vp, P(C.c_size_t)]),
+            'lrbms_project_plan_create_ws': (C.c_int, [vp, i32, vp, vp, C.c_size_t, P(vp)]),
             'lrbms_plan_run': (C.c_int, [vp, vp]),
             'lrbms_plan_destroy': (C.c_int, [vp]),
             'lrbms_plan_info': (C.c_int, [vp, i32, P(dbl)]),
@@ -237,11 +240,24 @@ def make_spmm_plan(handle, descs, keepalive=()):
     return Plan(handle, p, keepalive)
 
 
-def make_project_plan(handle, descs, keepalive=()):
+def make_project_plan(handle, descs, keepalive=(), scratch_owner=None):
+    """``scratch_owner``: an object with a ``_proj_scratch`` attribute (a CUDA tensor or None).  The plan's scratch then
+    lives in that tensor (grown when too small, reused by the owner's later plans) instead of inside the plan."""
     arr = (ProjectDesc * len(descs))(*descs)
     p = C.c_void_p()
-    handle.check(handle.lib.lrbms_project_plan_create(handle.h, len(descs), C.cast(arr, C.c_void_p), C.byref(p)))
-    return Plan(handle, p, keepalive)
+    if scratch_owner is None:
+        handle.check(handle.lib.lrbms_project_plan_create(handle.h, len(descs), C.cast(arr, C.c_void_p), C.byref(p)))
+        return Plan(handle, p, keepalive)
+    import torch
+    need = C.c_size_t()
+    handle.check(handle.lib.lrbms_project_plan_scratch_bytes(len(descs), C.cast(arr, C.c_void_p), C.byref(need)))
+    buf = getattr(scratch_owner, '_proj_scratch', None)
+    if buf is None or buf.numel() * 8 < need.value:
+        buf = torch.empty(max(32, need.value // 8 + need.value // 32), dtype=torch.float64, device='cuda')
+        scratch_owner._proj_scratch = buf
+    handle.check(handle.lib.lrbms_project_plan_create_ws(handle.h, len(descs), C.cast(arr, C.c_void_p), ptr(buf),
+                                                         buf.numel() * 8, C.byref(p)))
+    return Plan(handle, p, list(keepalive) + [buf])
 
 
 class Symbolic:

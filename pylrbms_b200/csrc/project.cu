@@ -770,9 +770,38 @@ int lrbms_spmm_plan_create(lrbms_handle_t h, int32_t n_desc, const lrbms_spmm_de
   return LRBMS_OK;
 }
 
+static inline bool two_step(const lrbms_project_desc_t& d) {
+  return d.rowptr && !(d.NL <= 8 * kMaxTile && d.NR <= 8 * kMaxTile);
+}
+static inline size_t scratch_doubles(const lrbms_project_desc_t& d) {
+  const size_t n = (size_t)std::max(1, d.n_rows) * (size_t)((d.NR + 3) & ~3);
+  return (n + 31) & ~(size_t)31;
+}
+
+int lrbms_project_plan_scratch_bytes(int32_t n_desc, const lrbms_project_desc_t* descs_host, size_t* bytes) {
+  if (!bytes || n_desc < 0 || (n_desc && !descs_host)) return LRBMS_ERR_INVALID;
+  size_t n = 0;
+  for (int i = 0; i < n_desc; ++i)
+    if (two_step(descs_host[i])) n += scratch_doubles(descs_host[i]);
+  *bytes = n * sizeof(double);
+  return LRBMS_OK;
+}
+
 int lrbms_project_plan_create(lrbms_handle_t h, int32_t n_desc, const lrbms_project_desc_t* descs_host,
                               lrbms_plan_t* out) {
+  return lrbms_project_plan_create_ws(h, n_desc, descs_host, nullptr, 0, out);
+}
+
+int lrbms_project_plan_create_ws(lrbms_handle_t h, int32_t n_desc, const lrbms_project_desc_t* descs_host, void* scratch,
+                                 size_t scratch_bytes, lrbms_plan_t* out) {
   LRBMS_REQUIRE(h, h && out && (n_desc == 0 || descs_host), "project_plan_create: null argument");
+  if (scratch) {
+    size_t need = 0;
+    lrbms_project_plan_scratch_bytes(n_desc, descs_host, &need);
+    LRBMS_REQUIRE(h, scratch_bytes >= need && ((uintptr_t)scratch & 255) == 0,
+                  "project_plan_create_ws: scratch too small or misaligned (see lrbms_project_plan_scratch_bytes)");
+  }
+  size_t scratch_pos = 0;
   LRBMS_CUDA_CHECK(h, cudaSetDevice(h->device));
   for (int i = 0; i < n_desc; ++i) {
     const auto& d = descs_host[i];
@@ -796,13 +825,17 @@ int lrbms_project_plan_create(lrbms_handle_t h, int32_t n_desc, const lrbms_proj
     x.rowptr = d.rowptr; x.colind = d.colind; x.values = d.values; x.n_rows = d.n_rows; x.n_cols = d.n_cols;
     x.VL = d.VL; x.ldl = d.ldl; x.NL = d.NL; x.VR = d.VR; x.ldr = d.ldr; x.NR = d.NR; x.out = d.out; x.ldo = d.ldo;
     x.alpha = d.alpha;
-    const bool fits = d.NL <= 8 * kMaxTile && d.NR <= 8 * kMaxTile;
-    if (d.rowptr && !fits) {
+    if (two_step(d)) {
       // W = A VR into scratch, then G = VL^T W with the dense kernel
       double* W = nullptr;
       const int ldw = (d.NR + 3) & ~3;
-      rc = plan_alloc(P, &W, (size_t)std::max(1, d.n_rows) * ldw);
-      if (rc) break;
+      if (scratch) {
+        W = reinterpret_cast<double*>(scratch) + scratch_pos;
+        scratch_pos += scratch_doubles(d);
+      } else {
+        rc = plan_alloc(P, &W, (size_t)std::max(1, d.n_rows) * ldw);
+        if (rc) break;
+      }
       lrbms_spmm_desc_t sd{d.rowptr, d.colind, d.values, d.n_rows, d.n_cols, d.VR, d.ldr, d.NR, W, ldw};
       spmm_descs.push_back(sd);
       x.rowptr = nullptr; x.colind = nullptr; x.values = nullptr; x.n_cols = d.n_rows;

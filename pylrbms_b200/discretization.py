@@ -206,4 +206,6 @@ def discretize(data, alpha_returns_first=True):
                                   name=data.meta.get('problem'))
     info = {'num_subdomains': S, 'neighborhoods': data.neighborhoods, 'n': data.n, 'm': data.m,
             'local_products': [operators['local_energy_dg_product_{}'.format(i)] for i in range(S)]}
+    from .reductor import prepare_operators
+    prepare_operators(d)              # symmetry flags, fused chain products, transposes: operator-only, done once here
     return d, info

@@ -159,10 +159,17 @@ class _ArrayRef:
         self.labels = labels if labels is not None else \
             np.stack([np.full(int(N), -1), np.zeros(int(N), dtype=np.int64), np.arange(int(N))], axis=1).astype(np.int64)
 
+    _of_cache = {}
+
     @staticmethod
     def of(arr):
-        return _ArrayRef(arr.device_ptr, arr.ld, len(arr), arr.dim, arr, key=getattr(arr, '_plan_key', None),
-                         labels=getattr(arr, '_plan_labels', None))
+        """Reference of a vector array; cached by object for the duration of one ``build_plan`` (cleared there)."""
+        hit = _ArrayRef._of_cache.get(id(arr))
+        if hit is None or hit.keep is not arr:
+            hit = _ArrayRef._of_cache[id(arr)] = _ArrayRef(arr.device_ptr, arr.ld, len(arr), arr.dim, arr,
+                                                           key=getattr(arr, '_plan_key', None),
+                                                           labels=getattr(arr, '_plan_labels', None))
+        return hit
 
 
 def _labels(k, qs, n):
@@ -193,19 +200,37 @@ class _Planner:
         self.owner_rank_of = owner_rank_of or (lambda owner: 0)
         self.rank, self.world = rank, world
         self.scratch_pool, self.scratch_used = None, []
+        self._arena, self.arena_block = [], 64 * 1024 * 1024          # arena blocks of 64 Mi doubles (512 MB)
+        self.scratch_owner = None     # the reductor: keeps one projection scratch buffer for all of its plans
+        self.timings = {}
         self._region_sizes = [0] * world
         self._pending = []            # deferred allocations: (owner_rank, size) -> resolved into offsets at finalize
 
     def _scratch(self, rows, ld):
-        """Scratch arrays are recycled from the previous plan of the same reductor (same sizes after most enrichments)."""
-        torch = _torch()
+        """Scratch arrays are carved out of a few large arena blocks (one device allocation per 512 MB instead of one per
+        array: 192 arrays at 8 x 8 subdomains) and recycled from the previous plan of the same reductor."""
         pool = self.scratch_pool
         key = (rows, ld)
         if pool is not None and pool.get(key):
             t = pool[key].pop()
         else:
-            t = torch.empty((rows, ld), dtype=torch.float64, device='cuda')
+            t = self._arena_take(rows * ld).view(rows, ld)
         self.scratch_used.append((key, t))
+        return t
+
+    def _arena_take(self, n, zero=False):
+        """``n`` doubles from the current arena block (32-double aligned); a new block when it is exhausted."""
+        torch = _torch()
+        n_al = (int(n) + 31) // 32 * 32
+        blk = self._arena[-1] if self._arena else None
+        if blk is None or blk[1] + n_al > blk[0].numel():
+            size = max(n_al, self.arena_block)
+            blk = [torch.empty(size, dtype=torch.float64, device='cuda'), 0]
+            self._arena.append(blk)
+        t = blk[0][blk[1]:blk[1] + int(n)]
+        blk[1] += n_al
+        if zero:
+            t.zero_()
         return t
 
     # -- output allocation: grouped per owner rank so that each rank's results are one contiguous region
@@ -385,8 +410,13 @@ class _Planner:
         for (token, csr, n_rows, L, R, ldo, alpha, sym) in self.jobs:
             descs.append(project_desc(csr, n_rows, L.ptr, L.ld, L.N, R.ptr, R.ld, R.N, base + 8 * int(self.offsets[token]),
                                       ldo, alpha, symmetric=sym))
+        import time as _time
+        _t = _time.perf_counter()
         self.spmm_plans = [make_spmm_plan(self.h, st, []) for st in self.spmm_stages if st]
-        self.project_plan = make_project_plan(self.h, descs, []) if descs else None
+        self.timings['spmm_plan_create_s'] = _time.perf_counter() - _t
+        _t = _time.perf_counter()
+        self.project_plan = make_project_plan(self.h, descs, [], scratch_owner=self.scratch_owner) if descs else None
+        self.timings['project_plan_create_s'] = _time.perf_counter() - _t
         self.n_project_descs = len(descs)
         self.n_spmm_descs = sum(len(st) for st in self.spmm_stages)
         self.n_incremental_jobs = len(self.inc_jobs)
@@ -480,9 +510,27 @@ def _selection(op, bases):
     return None
 
 
+_DIMS_CACHE = {}
+_SPACE_TOKENS = {}
+
+
 def _dims(space, bases):
-    subs = space.subspaces if hasattr(space, 'subspaces') else [space]
-    return [1 if s.id == 'SCALARS' else len(bases[s.id]) for s in subs]
+    """Basis sizes over the subspaces of ``space``.  Hundreds of operators carry their own (equal) block-space objects with
+    one subspace per subdomain, so the sizes are cached per *subspace-id tuple* (interned once per space object) for the
+    duration of one ``build_plan`` (cleared there) instead of being recomputed O(S) times per operator."""
+    token = getattr(space, '_dims_token', None)
+    if token is None:
+        subs = space.subspaces if hasattr(space, 'subspaces') else [space]
+        token = _SPACE_TOKENS.setdefault(tuple(s.id for s in subs), len(_SPACE_TOKENS))
+        try:
+            space._dims_token = token
+        except AttributeError:
+            pass
+    hit = _DIMS_CACHE.get(token)
+    if hit is None:
+        subs = space.subspaces if hasattr(space, 'subspaces') else [space]
+        hit = _DIMS_CACHE[token] = [1 if s.id == 'SCALARS' else len(bases[s.id]) for s in subs]
+    return hit
 
 
 def plan_projection(op, bases, planner, owner=None, name=None):
@@ -553,17 +601,7 @@ def _plan_chain(op, bases, planner, owner, name):
     #      life of the reductor -- the operators are static -- so the chain costs one SpMM and, for r_dd, a Gram over the
     #      m_i flux dofs instead of the n_i DG dofs.  Same result up to the order of summation.
     if len(chain) >= 2 and planner.fuse_cache is not None:
-        key = tuple(id(m.csr) for m in chain)
-        if key not in planner.fuse_cache:
-            from .kernels import DeviceCsr
-            P = chain[0].csr.host
-            for m in chain[1:]:
-                P = P @ m.csr.host
-            P = P.tocsr()
-            P.sort_indices()
-            planner.fuse_cache[key] = (CsrOperator(DeviceCsr(P), source_id=chain[-1].source.id, range_id=chain[0].range.id,
-                                                   name='fused_chain'), [m.csr for m in chain])
-        chain = [planner.fuse_cache[key][0]]
+        chain = [fuse_chain(chain, planner.fuse_cache)]
     # ---- (A^T ...)-prefix: L^T A^T = (A L)^T, one SpMM on the left array (shared with the right side through the cache)
     while len(chain) > 1 and chain[0].transposed_of is not None:
         L = planner.spmm(owner, chain[0].transposed_of.csr, L)
@@ -583,6 +621,62 @@ def _plan_chain(op, bases, planner, owner, name):
     return ReducedBlockOperator(planner, [SuperBlock(row_idx, col_idx, token, sum(row_sizes), sum(col_sizes),
                                                      row_sizes, col_sizes)],
                                 rdims, _dims(op.source, bases), name=op.name or name, functional=functional)
+
+
+def _walk_csr(op, out):
+    """All CsrOperators reachable from ``op`` (Lincomb / Block / Concatenation containers)."""
+    if isinstance(op, CsrOperator):
+        out.append(op)
+    elif isinstance(op, (LincombOperator, Concatenation)):
+        for o in op.operators:
+            _walk_csr(o, out)
+    elif isinstance(op, BlockOperator):
+        for b in op._blocks.ravel():
+            if b is not None:
+                _walk_csr(b, out)
+    return out
+
+
+def fuse_chain(chain, cache):
+    """The product of consecutive sparse matrices of an operator chain, formed once and cached (key: the matrices)."""
+    key = tuple(id(m.csr) for m in chain)
+    if key not in cache:
+        from .kernels import DeviceCsr
+        P = chain[0].csr.host
+        for m in chain[1:]:
+            P = P @ m.csr.host
+        P = P.tocsr()
+        P.sort_indices()
+        cache[key] = (CsrOperator(DeviceCsr(P), source_id=chain[-1].source.id, range_id=chain[0].range.id, name='fused_chain'),
+                      [m.csr for m in chain])
+    return cache[key][0]
+
+
+def prepare_operators(d):
+    """One-off preparation that depends on the operators only -- done when the discretization is built, not in the first
+    ``reduce()``: symmetry flags of the square matrices (a symmetric Gram is computed on its lower output chunks only), the
+    products of chained sparse matrices (``r_dd``: ``D^T M D``) and the transposes that chains with a narrow left side apply
+    to that side (``df_ab``, ``r_fd``).  All three are cached on the matrices / on ``d`` and shared by every reductor of ``d``."""
+    cache = d.__dict__.setdefault('_fused_chains', {})
+    ops = list(d.operators.values()) + list(d.products.values())
+    for op in ops:
+        for c in _walk_csr(op, []):
+            if c.csr.shape[0] == c.csr.shape[1]:
+                c.csr.symmetric
+        for cc in ([op] if isinstance(op, Concatenation) else
+                   [o for o in getattr(op, 'operators', []) if isinstance(o, Concatenation)]):
+            chain = [m for m in cc.flat() if isinstance(m, CsrOperator)]
+            flat = cc.flat()
+            if len(chain) >= 2 and all(isinstance(m, CsrOperator) for m in flat[1:-1]) and len(chain) == len(flat) - 2:
+                fused = fuse_chain(chain, cache)
+                if fused.csr.shape[0] == fused.csr.shape[1]:
+                    fused.csr.symmetric
+                chain = [fused]
+            # narrow left end (a functional or a single subspace) against a neighbourhood on the right: (A^T L)^T R
+            left = flat[0]
+            narrow = isinstance(left, (VectorFunctional, BlockProjectionOperator, BlockEmbeddingOperator))
+            if narrow and len(chain) == 1:
+                chain[0].csr.T
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -632,8 +726,11 @@ class LRBMSReductor(GenericRBSystemReductor):
                 all(len(self.bases[s.id]) >= n for s, n in zip(subs, old.block_dims)):
             prev = old
         planner = _Planner(Handle.get(), owner_rank_of, rank, world, prev=prev)
+        planner.scratch_owner = self
+        _DIMS_CACHE.clear()
+        _ArrayRef._of_cache.clear()
         if self.fuse_chains:
-            planner.fuse_cache = self.__dict__.setdefault('_fused_chains', {})
+            planner.fuse_cache = d.__dict__.setdefault('_fused_chains', {})      # shared with prepare_operators(d)
         planner.narrow_left = self.narrow_left
         if old is not None and getattr(old, 'reusable', False):
             # the reduced model of the previous plan is no longer referenced: recycle its scratch arrays
@@ -659,23 +756,30 @@ class LRBMSReductor(GenericRBSystemReductor):
             for i in nbh[k]:
                 targets[i].append(k)
         oi_slab, rt_slab, oi_col, rt_col = [], [], [], []
+        shapes, total = [], 0
         for i in range(S):
             cols = np.concatenate([[0], np.cumsum([N[k] for k in targets[i]])]).astype(int)
             oi_col.append(dict(zip(targets[i], cols[:-1])))
             rt_col.append(dict(zip(targets[i], Q * cols[:-1])))
             ld_o = max(4, (cols[-1] + 3) // 4 * 4)
             ld_r = max(4, (Q * cols[-1] + 3) // 4 * 4)
-            oi_slab.append(torch.zeros((subs[i].dim, ld_o), dtype=torch.float64, device='cuda'))
             m_i = fr.operators[0]._blocks[i, i].range.subspaces[nbh[i].index(i)].dim
-            rt_slab.append(torch.zeros((m_i, ld_r), dtype=torch.float64, device='cuda'))
+            shapes.append((subs[i].dim, ld_o, m_i, ld_r, total))
+            total += (subs[i].dim * ld_o + 31) // 32 * 32 + (m_i * ld_r + 31) // 32 * 32
+        slab_buf = torch.zeros(max(1, total), dtype=torch.float64, device='cuda')      # one allocation, one memset
+        for (n_i, ld_o, m_i, ld_r, pos) in shapes:
+            oi_slab.append(slab_buf[pos:pos + n_i * ld_o].view(n_i, ld_o))
+            pos += (n_i * ld_o + 31) // 32 * 32
+            rt_slab.append(slab_buf[pos:pos + m_i * ld_r].view(m_i, ld_r))
         for k in range(S):
             oi_k = oi._blocks[k, k]
             comps_o, comps_r = [], []
             n0, n1 = N_old[k], N[k]                               # columns [0, n0) exist in the previous plan's slabs
+            lab_o, lab_r = _labels(k, [0], N[k]), _labels(k, range(Q), N[k])
             for c, i in enumerate(nbh[k]):
                 view_o = oi_slab[i][:, oi_col[i][k]:oi_col[i][k] + N[k]]
                 arr_o = oi_k.range.subspaces[c].from_dofmajor(view_o, N[k])
-                arr_o._plan_key, arr_o._plan_labels = ('oi', i, k), _labels(k, [0], N[k])
+                arr_o._plan_key, arr_o._plan_labels = ('oi', i, k), lab_o
                 comps_o.append(arr_o)
                 if prev is not None and n0:
                     pc = prev.oi_col[i][k]
@@ -686,7 +790,7 @@ class LRBMSReductor(GenericRBSystemReductor):
                 view_r = rt_slab[i][:, rt_col[i][k]:rt_col[i][k] + Q * N[k]]
                 rt_space = fr.operators[0]._blocks[k, k].range.subspaces[c]
                 arr_r = rt_space.from_dofmajor(view_r, Q * N[k])
-                arr_r._plan_key, arr_r._plan_labels = ('rt', i, k), _labels(k, range(Q), N[k])
+                arr_r._plan_key, arr_r._plan_labels = ('rt', i, k), lab_r
                 comps_r.append(arr_r)
                 for q in range(Q):                               # q-major ordering of the RT basis (reductor.py:55-60)
                     fr_kq = fr.operators[q]._blocks[k, k]
@@ -699,7 +803,7 @@ class LRBMSReductor(GenericRBSystemReductor):
             self.bases[oi.range.subspaces[k].id] = BlockVectorArray(comps_o, oi.range.subspaces[k])
             self.bases[fr.range.subspaces[k].id] = BlockVectorArray(comps_r, fr.range.subspaces[k])
         planner.oi_slab, planner.rt_slab, planner.oi_col, planner.rt_col = oi_slab, rt_slab, oi_col, rt_col
-        planner.keep += [oi_slab, rt_slab]
+        planner.keep += [oi_slab, rt_slab, slab_buf]
 
         # ---- every operator and product of the discretization (reference reductor.py:70 -> GenericRBSystemReductor._reduce)
         red_ops, red_products = {}, {}
@@ -711,7 +815,10 @@ class LRBMSReductor(GenericRBSystemReductor):
             red_ops[name] = plan_projection(op, self.bases, planner, owner, name)
         for name, op in d.products.items():
             red_products[name] = plan_projection(op, self.bases, planner, None, name)
+        import time as _time
+        _t = _time.perf_counter()
         planner.finalize()
+        planner.timings['finalize_s'] = _time.perf_counter() - _t
         planner.block_dims = N
         planner.red_ops, planner.red_products = red_ops, red_products
         self.last_plan = planner
@@ -730,7 +837,10 @@ class LRBMSReductor(GenericRBSystemReductor):
             # returned earlier shares the plan's output buffer and is overwritten by this run.
             planner = self.last_plan
         else:
+            import time as _time
+            _t = _time.perf_counter()
             planner = self.build_plan(incremental=self.incremental)
+            planner.timings['build_plan_s'] = _time.perf_counter() - _t
             self._last_key = key
         planner.run()
         planner.exchange()
