@@ -141,8 +141,12 @@ int lrbms_project_plan_create(lrbms_handle_t h, int32_t n_desc, const lrbms_proj
  * descriptor list needs, lrbms_project_plan_create_ws carves the W arrays out of `scratch` (device, 256-byte aligned, must
  * outlive the plan; plans that never run concurrently may share it) instead of allocating them. */
 int lrbms_project_plan_scratch_bytes(int32_t n_desc, const lrbms_project_desc_t* descs_host, size_t* bytes);
+/* unit_rows_hint > 0: the amount of work (sum over descriptors of output chunks x rows, 3x for the wide dense Grams) the
+ * row partition is sized for, instead of the sum over this plan's own descriptors.  A rank that projects only its share of a
+ * descriptor list passes the figure of the WHOLE list: the rows of every descriptor are then cut exactly as in the
+ * unsharded plan and the results are bit-identical to it (the partial sums of a block are added in partition order). */
 int lrbms_project_plan_create_ws(lrbms_handle_t h, int32_t n_desc, const lrbms_project_desc_t* descs_host, void* scratch,
-                                 size_t scratch_bytes, lrbms_plan_t* out);
+                                 size_t scratch_bytes, int64_t unit_rows_hint, lrbms_plan_t* out);
 
 /* Incremental re-projection after an enrichment.  The reference re-runs the whole        */
 /* reductor.reduce() after every enrichment (online_enrichment.py:49-51); only the rows / columns that belong to the      */

@@ -108,7 +108,7 @@ def load_library():
             'lrbms_spmm_plan_create': (C.c_int, [vp, i32, vp, P(vp)]),
             'lrbms_project_plan_create': (C.c_int, [vp, i32, vp, P(vp)]),
             'lrbms_project_plan_scratch_bytes': (C.c_int, [i32, vp, P(C.c_size_t)]),
-            'lrbms_project_plan_create_ws': (C.c_int, [vp, i32, vp, vp, C.c_size_t, P(vp)]),
+            'lrbms_project_plan_create_ws': (C.c_int, [vp, i32, vp, vp, C.c_size_t, i64, P(vp)]),
             'lrbms_plan_run': (C.c_int, [vp, vp]),
             'lrbms_plan_destroy': (C.c_int, [vp]),
             'lrbms_plan_info': (C.c_int, [vp, i32, P(dbl)]),
@@ -240,13 +240,14 @@ def make_spmm_plan(handle, descs, keepalive=()):
     return Plan(handle, p, keepalive)
 
 
-def make_project_plan(handle, descs, keepalive=(), scratch_owner=None):
+def make_project_plan(handle, descs, keepalive=(), scratch_owner=None, unit_rows_hint=0):
     """``scratch_owner``: an object with a ``_proj_scratch`` attribute (a CUDA tensor or None).  The plan's scratch then
     lives in that tensor (grown when too small, reused by the owner's later plans) instead of inside the plan."""
     arr = (ProjectDesc * len(descs))(*descs)
     p = C.c_void_p()
     if scratch_owner is None:
-        handle.check(handle.lib.lrbms_project_plan_create(handle.h, len(descs), C.cast(arr, C.c_void_p), C.byref(p)))
+        handle.check(handle.lib.lrbms_project_plan_create_ws(handle.h, len(descs), C.cast(arr, C.c_void_p), None, 0,
+                                                             int(unit_rows_hint), C.byref(p)))
         return Plan(handle, p, keepalive)
     import torch
     need = C.c_size_t()
@@ -256,7 +257,7 @@ def make_project_plan(handle, descs, keepalive=(), scratch_owner=None):
         buf = torch.empty(max(32, need.value // 8 + need.value // 32), dtype=torch.float64, device='cuda')
         scratch_owner._proj_scratch = buf
     handle.check(handle.lib.lrbms_project_plan_create_ws(handle.h, len(descs), C.cast(arr, C.c_void_p), ptr(buf),
-                                                         buf.numel() * 8, C.byref(p)))
+                                                         buf.numel() * 8, int(unit_rows_hint), C.byref(p)))
     return Plan(handle, p, list(keepalive) + [buf])
 
 

@@ -31,6 +31,10 @@ struct ProjItem {
   int32_t group_size;
   int32_t mirror;     // symmetric descriptor, off-diagonal chunk pair: also write the transposed chunk
   int32_t diag;       // gram_kernel: diagonal chunk of a symmetric descriptor (VL and VR chunks are the same columns)
+  int32_t nl, nr;     // extent of the output chunk this item owns.  A gram CTA computes 2 x 2 quadrants of whole tiles and can
+                      // cover more columns than its chunk has (7 tiles -> quadrants of 4 + 4); it must not store them: the
+                      // neighbouring chunk owns those entries, and where that one is a *mirrored* chunk its values differ in
+                      // the last bit (v_a^T A v_b vs v_b^T A v_a), which made the stored result depend on the write order
 };
 
 struct DevDesc {       // device-side mirror of lrbms_project_desc_t (VR/rowptr possibly redirected to scratch)
@@ -292,7 +296,7 @@ gram_kernel(const ProjItem* __restrict__ items, const DevDesc* __restrict__ desc
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, t = lane & 3;
   const int wm = warp >> 1, wn = warp & 1;
-  const int nl = min(16 * WM, D.NL - it.l0), nr = min(16 * WN, D.NR - it.c0);
+  const int nl = min(it.nl, D.NL - it.l0), nr = min(it.nr, D.NR - it.c0);
   const bool diag = it.diag != 0;                       // VL and VR chunks are the same columns: stage them once
   const double* __restrict__ gL = D.VL + it.l0;
   const double* __restrict__ gR = D.VR + it.c0;
@@ -789,11 +793,11 @@ int lrbms_project_plan_scratch_bytes(int32_t n_desc, const lrbms_project_desc_t*
 
 int lrbms_project_plan_create(lrbms_handle_t h, int32_t n_desc, const lrbms_project_desc_t* descs_host,
                               lrbms_plan_t* out) {
-  return lrbms_project_plan_create_ws(h, n_desc, descs_host, nullptr, 0, out);
+  return lrbms_project_plan_create_ws(h, n_desc, descs_host, nullptr, 0, 0, out);
 }
 
 int lrbms_project_plan_create_ws(lrbms_handle_t h, int32_t n_desc, const lrbms_project_desc_t* descs_host, void* scratch,
-                                 size_t scratch_bytes, lrbms_plan_t* out) {
+                                 size_t scratch_bytes, int64_t unit_rows_hint, lrbms_plan_t* out) {
   LRBMS_REQUIRE(h, h && out && (n_desc == 0 || descs_host), "project_plan_create: null argument");
   if (scratch) {
     size_t need = 0;
@@ -856,6 +860,7 @@ int lrbms_project_plan_create_ws(lrbms_handle_t h, int32_t n_desc, const lrbms_p
     int64_t chunks = (int64_t)((x.NL + cw - 1) / cw) * ((x.NR + cw - 1) / cw);
     unit_rows += chunks * x.n_rows * (is_gram(x) ? 3 : 1);     // a gram CTA does four times the work with one CTA per SM
   }
+  if (unit_rows_hint > 0) unit_rows = unit_rows_hint;
   const int64_t target_ctas = (int64_t)h->sm_count * 12;
   int64_t rows_per_cta = std::max<int64_t>(128, ((unit_rows / std::max<int64_t>(1, target_ctas) + 31) / 32) * 32);
   rows_per_cta = std::min<int64_t>(rows_per_cta, 2048);
@@ -896,6 +901,7 @@ int lrbms_project_plan_create_ws(lrbms_handle_t h, int32_t n_desc, const lrbms_p
           it.group = group; it.slot = slot++; it.group_size = 0;
           it.mirror = (symmetric && rc_ != lc) ? 1 : 0;
           it.diag = (gram && symmetric && rc_ == lc && x.VL == x.VR && x.ldl == x.ldr) ? 1 : 0;
+          it.nl = 8 * (lt1 - lt0); it.nr = 8 * (rt1 - rt0);
           bucket.push_back(it);
         }
         for (size_t k = first; k < bucket.size(); ++k) bucket[k].group_size = slot;

@@ -202,6 +202,7 @@ class _Planner:
         self.scratch_pool, self.scratch_used = None, []
         self._arena, self.arena_block = [], 64 * 1024 * 1024          # arena blocks of 64 Mi doubles (512 MB)
         self.scratch_owner = None     # the reductor: keeps one projection scratch buffer for all of its plans
+        self.unit_rows = 0
         self.timings = {}
         self._region_sizes = [0] * world
         self._pending = []            # deferred allocations: (owner_rank, size) -> resolved into offsets at finalize
@@ -263,6 +264,13 @@ class _Planner:
     def project(self, owner, csr, L, R, alpha=1.0):
         """Schedule ``alpha * L^T csr R`` (``csr=None``: identity); returns the output token (row-major ``L.N x R.N``)."""
         token = self.alloc(owner, L.N * R.N)
+        if L.N and R.N:
+            # work of this block in the units the library sizes its row partition with, summed over ALL ranks' blocks: every
+            # rank cuts the rows of a block exactly like the unsharded plan (bit-identical sharded results)
+            n_r = csr.shape[0] if csr is not None else L.dim
+            gram = L.N > 40 and R.N > 40
+            cw = 80 if gram else 40
+            self.unit_rows += (-(-L.N // cw)) * (-(-R.N // cw)) * n_r * (3 if gram else 1)
         key = (id(csr) if csr is not None else None, L.key, R.key, float(alpha))
         self.job_index[key] = (token, L.labels, R.labels)
         if L.N and R.N and self.mine(owner):
@@ -415,7 +423,8 @@ class _Planner:
         self.spmm_plans = [make_spmm_plan(self.h, st, []) for st in self.spmm_stages if st]
         self.timings['spmm_plan_create_s'] = _time.perf_counter() - _t
         _t = _time.perf_counter()
-        self.project_plan = make_project_plan(self.h, descs, [], scratch_owner=self.scratch_owner) if descs else None
+        self.project_plan = make_project_plan(self.h, descs, [], scratch_owner=self.scratch_owner,
+                                              unit_rows_hint=self.unit_rows) if descs else None
         self.timings['project_plan_create_s'] = _time.perf_counter() - _t
         self.n_project_descs = len(descs)
         self.n_spmm_descs = sum(len(st) for st in self.spmm_stages)

@@ -332,3 +332,26 @@ def test_incremental_reprojection_matches_full(handle, num_subdomains, cells, ba
             e = U.data[k] - U2.data[k]
             assert np.sqrt(e @ A @ e) <= RTOL * np.sqrt(U2.data[k] @ A @ U2.data[k])
         assert np.abs(eta - eta2).max() <= RTOL * np.abs(eta2).max()
+
+
+def test_projection_is_bit_reproducible(handle):
+    """Two projections of the same bases -- the same plan run again, and a second reductor with its own buffers -- must agree
+    bit for bit.  120-column estimator Grams (three-member neighbourhoods, N = 20, Q = 2) split into output chunks of 7 + 8
+    tiles: a gram CTA covers 8 + 8 and once stored the surplus tile row, racing with the mirrored chunk that owns it."""
+    import torch
+    from pylrbms_b200 import LRBMSReductor
+    data, d_ref, red_ref, d, red = _setup((2, 2), 8, 20, 31)
+
+    def dense(rd):
+        return {(name, q): o.to_dense() for name, op in rd.operators.items() for q, o in enumerate(getattr(op, 'operators', [op]))}
+    rd = red.reduce()
+    A = dense(rd)
+    for _ in range(3):
+        red.last_plan.run()
+        torch.cuda.synchronize()
+        B = dense(rd)
+        assert all(np.array_equal(A[k], B[k]) for k in A)
+    bases = {'domain_%d' % k: red.bases['domain_%d' % k].to_numpy() for k in range(4)}
+    C_ = dense(LRBMSReductor(d, bases=bases).reduce())
+    bad = [k for k in A if not np.array_equal(A[k], C_[k])]
+    assert not bad, bad

@@ -19,9 +19,11 @@ def main():
     dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     from pylrbms_b200 import LRBMSReductor, discretize
     from pylrbms_b200.swipdg_fixture import assemble_block_swipdg, make_local_bases
-    data = assemble_block_swipdg((4, 4), 8)
-    bases = make_local_bases(data, [5 + (i % 4) for i in range(16)], seed=11)
-    bd = {'domain_%d' % i: bases[i] for i in range(16)}
+    sx, cells = int(os.environ.get('SUBDOMAINS', '4')), int(os.environ.get('CELLS', '8'))
+    data = assemble_block_swipdg((sx, sx), cells)
+    nb = os.environ.get('BASIS')
+    bases = make_local_bases(data, int(nb) if nb else [5 + (i % 4) for i in range(sx * sx)], seed=11)
+    bd = {'domain_%d' % i: bases[i] for i in range(sx * sx)}
     d, _ = discretize(data)
     red_u = LRBMSReductor(d, bases=bd)
     rd_u = red_u.reduce()
@@ -37,7 +39,11 @@ def main():
         for x, y in zip(ta, tb):
             A, B = x.to_dense(), y.to_dense()
             assert A.shape == B.shape
-            worst = max(worst, float(np.abs(A - B).max()))
+            diff = float(np.abs(A - B).max())
+            if diff > 0 and worst == 0.0:
+                print('first difference:', name, diff, 'scale', float(np.abs(A).max()), 'nonzero entries differing', int((A != B).sum()),
+                      'rows_per_cta hint', red_u.last_plan.unit_rows, red_s.last_plan.unit_rows)
+            worst = max(worst, diff)
     assert worst == 0.0, worst
     mine = red_s.last_plan.n_project_descs
     total = red_u.last_plan.n_project_descs
