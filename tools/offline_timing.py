@@ -1,6 +1,7 @@
 """Developer aid: time the offline projection plan of the bench workload (C2 by default) with CUDA events.
 
-    python tools/offline_timing.py [bench.py options] ; LRBMS_SINGLE_STREAM=1 serialises the buckets on one stream
+    python tools/offline_timing.py [bench.py options] ; SINGLE_STREAM=1 serialises the buckets on one stream
+    (lrbms_set_option(LRBMS_OPT_SINGLE_STREAM), e.g. for ncu captures)
 """
 import os, sys, numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -11,6 +12,10 @@ from pylrbms_b200 import LRBMSReductor, discretize
 a = bench.parse_args()
 data, bases = bench.make_inputs(a)
 d, _ = discretize(data)
+from pylrbms_b200._lib import Handle
+_h = Handle.get()
+_single = os.environ.get('SINGLE_STREAM', '0') not in ('', '0')
+_h.check(_h.lib.lrbms_set_option(_h.h, 1, 1 if _single else 0))
 reductor = LRBMSReductor(d, bases=bases)
 rd = reductor.reduce()
 torch.cuda.synchronize()
@@ -33,5 +38,5 @@ for _ in range(int(os.environ.get('REPS', '10'))):
 pp = planner.project_plan
 t = float(np.mean(tp)) * 1e-3
 print('single_stream=%s  all stages %.3f ms  projection plan %.3f ms (min %.3f)  %.0f GB/s (survey bytes)  %.2f TFLOP/s FP64' % (
-    os.environ.get('LRBMS_SINGLE_STREAM', '0'), np.mean(ta), np.mean(tp), np.min(tp), pp.algorithmic_bytes_survey / t / 1e9,
+    os.environ.get('SINGLE_STREAM', '0'), np.mean(ta), np.mean(tp), np.min(tp), pp.algorithmic_bytes_survey / t / 1e9,
     pp.flops / t / 1e12))
