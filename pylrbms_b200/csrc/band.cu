@@ -474,8 +474,11 @@ size_t lrbms_band_workspace_bytes(const lrbms_band_plan& B, int64_t n_mu) {
 
 int lrbms_band_solve(lrbms_context* ctx, const lrbms_band_plan& B, int64_t n_mu, const double* theta, double* u, int32_t* info,
                      void* workspace, size_t workspace_bytes, cudaStream_t s) {
-  const int64_t chunk = lrbms_band_chunk(B, n_mu, workspace_bytes);
-  if (chunk < 1) return lrbms_fail(ctx, LRBMS_ERR_INVALID, "online_solve: workspace too small (see lrbms_online_workspace_bytes)");
+  const int64_t max_chunk = lrbms_band_chunk(B, n_mu, workspace_bytes);
+  if (max_chunk < 1) return lrbms_fail(ctx, LRBMS_ERR_INVALID, "online_solve: workspace too small (see lrbms_online_workspace_bytes)");
+  // equal chunks (64 parameters with room for 57 factors: 32 + 32, not 57 + 7 -- a small tail chunk leaves most SMs idle)
+  const int64_t n_chunks = (n_mu + max_chunk - 1) / max_chunk;
+  const int64_t chunk = (n_mu + n_chunks - 1) / n_chunks;
   BandParams P = to_params(B);
   double* work = reinterpret_cast<double*>(workspace);
   const int n_theta = B.Q + B.Qf;

@@ -90,9 +90,25 @@ class BlockSwipdgDiscretization:
         for q in range(1, len(mats)):
             A = A + theta[q] * mats[q]
         opts = dict(inverse_options or {})
-        rtol = float(opts.get('rtol', 1e-12))
-        x, iters, relres = pcg_solve(DeviceCsr(A.tocsr()), f, rtol=rtol, max_iter=opts.get('maxiter'))
-        self.last_local_correction_info = {'iterations': iters, 'relative_residual': relres, 'size': int(A.shape[0])}
+        # CG to the requested recurrence residual, then restarts from the iterate: a restart recomputes the TRUE residual
+        # b - A x (the recurrence residual drifts away from it), so the iterate reaches the attainable accuracy eps * cond(A) of
+        # a direct solve -- what the reference's apply_inverse (dune-istl / a sparse direct solver) delivers.  The enriched
+        # reduced model then matches a direct-solve enrichment to ~1e-10 instead of the 1e-7 of a single CG run.
+        rtol = float(opts.get('rtol', 1e-13))
+        A_dev = DeviceCsr(A.tocsr())
+        x, iters, relres = pcg_solve(A_dev, f, rtol=rtol, max_iter=opts.get('maxiter'))
+        restarts = 0
+        for _ in range(int(opts.get('restarts', 3))):
+            x2, it2, rr2 = pcg_solve(A_dev, f, x0=x, rtol=0.1 * rtol, max_iter=opts.get('maxiter'))
+            restarts += 1
+            iters += it2
+            improved = rr2 < 0.5 * relres
+            if rr2 <= relres:
+                x, relres = x2, rr2
+            if it2 == 0 or not improved:
+                break
+        self.last_local_correction_info = {'iterations': iters, 'relative_residual': relres, 'size': int(A.shape[0]),
+                                           'restarts': restarts}
         if not relres <= rtol:
             # the reference's apply_inverse raises on solver failure; an unconverged corrector must not enter a basis
             from ._lib import LrbmsError

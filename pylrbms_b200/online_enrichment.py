@@ -69,6 +69,34 @@ class AdaptiveEnrichment:
     def estimate(self, U, mu, decompose=False):
         return self.rd.estimate(U, mu=mu, decompose=decompose)
 
+    def solve_batch(self, mus, enrichment_steps=np.inf, callback=None):
+        """Enrichment driven by a whole parameter batch (no counterpart in the reference, which handles one ``mu`` per
+        call, ``online_enrichment.py:63-93``): every pass sweeps ALL parameters in one ``rd.sweep`` (one launch set instead
+        of ``len(mus)`` solve / estimate calls), takes the parameter with the largest estimate, marks subdomains from ITS
+        indicators (Doerfler + age, the reference's rules), enriches with ITS solution and re-reduces; it stops when the
+        largest estimate over the batch is below ``target_error``.  Returns ``(U, eta, rd, reductor)`` for the final model,
+        ``U`` / ``eta`` covering the whole batch."""
+        mus = [self.discretization.parse_parameter(mu) for mu in mus]
+        age_count = np.ones(self._num_blocks)
+        step, local_problem_solves = 1, 0
+        from .reductor import ExtensionError
+        while True:
+            U, eta, _, indicators = self.rd.sweep(mus, decompose=True)
+            worst = int(np.argmax(eta))
+            if callback:
+                subs = self.reductor.d.solution_space.subspaces
+                callback(self.rd, U, mus, {'eta': eta, 'eta_max': float(eta[worst]), 'argmax': worst,
+                                           'local_problem_solves': local_problem_solves,
+                                           'global RB size': self.rd.solution_space.dim,
+                                           'local RB sizes': [len(self.reductor.bases[s.id]) for s in subs]})
+            if eta[worst] <= self.target_error or step > enrichment_steps:
+                return U, eta, self.rd, self.reductor
+            step += 1
+            try:
+                local_problem_solves = self._enrich_once(U[worst], mus[worst], indicators[:, worst], age_count)
+            except ExtensionError:
+                return U, eta, self.rd, self.reductor        # nothing new to add for the worst parameter
+
     def solve(self, mu, enrichment_steps=np.inf, callback=None):
         mu = self.discretization.parse_parameter(mu)
         enrichment_step = 1

@@ -7,6 +7,8 @@ tests compare the PCG neighbourhood solve with a sparse direct solve and the who
 import numpy as np
 import pytest
 
+ETA_TOL = 1e-9
+
 
 def _brute_force_doerfler(indicators, theta):
     sq = np.asarray(indicators, dtype=float) ** 2
@@ -112,9 +114,11 @@ def test_adaptive_enrichment_matches_oracle(handle, num_subdomains, cells):
     for a, b in zip(log, log_ref):
         assert a['local_problem_solves'] == b['local_problem_solves']
         assert a['global RB size'] == b['global RB size']
-        # next-row tolerance: the corrector comes from an iterative solve (relative residual 1e-12) and is then
-        # orthonormalised, so the enriched models agree to solver accuracy, not to 1e-10
-        assert abs(a['eta'] - b['eta']) <= 1e-7 * abs(b['eta'])
+        # the corrector comes from restarted CG (true residual 1e-13 of ||b||, i.e. the attainable accuracy of the oracle's
+        # sparse direct solve) and is then orthonormalised and projected: 1e-10 tolerance like the rest of the path plus
+        # the conditioning of the corrector problem (both solvers carry eps * cond(A_nbh) ~ 1e-11 of their own)
+        worst_eta = max(locals().get('worst_eta', 0.0), abs(a['eta'] - b['eta']) / abs(b['eta']))
+        assert abs(a['eta'] - b['eta']) <= ETA_TOL * abs(b['eta'])
     assert rd.block_dims == rd_ref.block_dims
     from pylrbms_b200 import ExtensionError
     with pytest.raises(ExtensionError):          # same parameter again: nothing new to add (reference behaviour)
@@ -122,5 +126,44 @@ def test_adaptive_enrichment_matches_oracle(handle, num_subdomains, cells):
     # the enriched reduced solutions describe the same fine-scale function
     u_fine = red.reconstruct(U).to_numpy()[0]
     u_fine_ref = np.concatenate([b.data[0] for b in red_ref.reconstruct(U_ref)._blocks])
-    assert np.abs(u_fine - u_fine_ref).max() <= 1e-7 * np.abs(u_fine_ref).max()
-    assert d.last_local_correction_info['relative_residual'] <= 1e-12
+    print('enrichment parity: worst eta rel diff', worst_eta, 'fine-scale max rel diff',
+          np.abs(u_fine - u_fine_ref).max() / np.abs(u_fine_ref).max(), d.last_local_correction_info)
+    assert np.abs(u_fine - u_fine_ref).max() <= 10 * ETA_TOL * np.abs(u_fine_ref).max()
+    assert d.last_local_correction_info['relative_residual'] <= 1e-13
+
+
+@pytest.mark.gpu
+def test_batched_enrichment(handle):
+    """``AdaptiveEnrichment.solve_batch``: one sweep per pass over the whole parameter batch, enrichment from the worst
+    parameter.  A batch of one must retrace ``solve`` exactly; on a real batch the largest estimate over the batch must be
+    what every pass reports, the bases must grow, and the final model must reproduce a fresh sweep."""
+    from pylrbms_b200 import LRBMSReductor, discretize
+    from pylrbms_b200.online_enrichment import AdaptiveEnrichment
+    from pylrbms_b200.swipdg_fixture import assemble_block_swipdg, spe10_like_problem
+    data = assemble_block_swipdg((3, 3), 4, problem=spe10_like_problem(seed=7, contrast=50.0))
+    S = data.num_subdomains
+
+    def fresh():
+        d, _ = discretize(data)
+        red = LRBMSReductor(d, products=[d.operators['local_energy_dg_product_%d' % i] for i in range(S)], order=0)
+        return d, red, AdaptiveEnrichment(None, d, d.solution_space, red, red.reduce(), 1e-12, 0.5, 2)
+    # batch of one == the reference-shaped loop
+    _, _, ae1 = fresh()
+    log1 = []
+    ae1.solve(0.4, enrichment_steps=1, callback=lambda rd_, U, mu_, info: log1.append(info))
+    _, _, ae2 = fresh()
+    log2 = []
+    ae2.solve_batch([0.4], enrichment_steps=1, callback=lambda rd_, U, mu_, info: log2.append(info))
+    assert len(log1) == len(log2) == 2
+    for a, b in zip(log1, log2):
+        assert a['global RB size'] == b['global RB size'] and a['eta'] == b['eta'][0]
+    # a real batch
+    _, red, ae = fresh()
+    mus = np.linspace(0.15, 0.9, 9)
+    log = []
+    U, eta, rd, red_out = ae.solve_batch(mus, enrichment_steps=2, callback=lambda rd_, U_, mu_, info: log.append(info))
+    assert red_out is red and len(log) == 3 and len(U) == len(mus)
+    assert all(info['eta_max'] == info['eta'].max() and info['argmax'] == int(np.argmax(info['eta'])) for info in log)
+    assert log[-1]['global RB size'] > log[0]['global RB size']
+    U2, eta2 = rd.sweep(mus)
+    assert np.array_equal(eta2, eta) and np.array_equal(U2.data, U.data)
