@@ -199,6 +199,17 @@ int lrbms_symbolic_info(lrbms_symbolic_t s, int32_t what, int64_t* out);
  * returns number of int32 written (<= cap) or a negative status */
 int64_t lrbms_symbolic_get(lrbms_symbolic_t s, int32_t which, int32_t* out, int64_t cap);
 
+/* Panel schedule of the two-column shared-memory kernel (solve_kernel_v3), built from a tile schedule; host-only.  Exposed so
+ * that tests can execute the tables on the CPU.  info: 0 schedule applies (1) or not (0), 1 panels, 2 window slots, 3
+ * accumulator rows, 4 partial blocks, 5 tiles of the closed pattern, 6 DMMA flops per parameter, 7 / 8 int32 words per
+ * owner / panel record, 9 steps.  get: 0 col_ptr, 1 row_idx, 2 a_map, 3 win_slot, 4 owner records, 5 panel records, 6 steps
+ * (record layouts: csrc/symbolic3.h). */
+typedef struct lrbms_symbolic3* lrbms_symbolic3_t;
+int lrbms_symbolic3_create(lrbms_symbolic_t s, lrbms_symbolic3_t* out);
+int lrbms_symbolic3_destroy(lrbms_symbolic3_t s);
+int lrbms_symbolic3_info(lrbms_symbolic3_t s, int32_t what, int64_t* out);
+int64_t lrbms_symbolic3_get(lrbms_symbolic3_t s, int32_t which, int32_t* out, int64_t cap);
+
 /* one estimator term:  out[kind][sub][mu] += coef * theta[qa](mu) * theta[qb](mu) * xl^T M xr  */
 enum { LRBMS_VEC_ONE = 0, LRBMS_VEC_UI = 1, LRBMS_VEC_UN = 2, LRBMS_VEC_UR = 3 };
 enum { LRBMS_OUT_NC = 0, LRBMS_OUT_R = 1, LRBMS_OUT_DF = 2 };

@@ -51,10 +51,10 @@ __device__ __forceinline__ double* band_block(double* base, const BandParams& P,
 //  8 warps as 4 (rows) x 2 (columns): a warp owns 16 x 32 of the target = 2 x 4 DMMA tiles.
 // ------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kUpdThreads, 2)
-band_update_kernel(BandParams P, int J, const double* __restrict__ theta, double* __restrict__ work) {
+band_update_kernel(BandParams P, int J, int d0, const double* __restrict__ theta, double* __restrict__ work) {
   extern __shared__ __align__(128) double smem[];
   __shared__ __align__(8) unsigned long long full_bar[kUpdStages];
-  const int d = blockIdx.x, I = J + d;
+  const int d = d0 + blockIdx.x, I = J + d;
   if (I >= P.nbc) return;
   const int64_t mu = blockIdx.y;
   double* base = work + mu * P.per_mu;
@@ -455,8 +455,19 @@ int lrbms_band_build(lrbms_plan* plan, lrbms_band_plan& B, int32_t n_sub, const 
   cudaError_t e = cudaFuncSetAttribute(band_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B.upd_smem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(band_potrf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B.potrf_smem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(band_trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B.trsm_smem);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&B.side, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&B.ev_diag, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&B.ev_potrf, cudaEventDisableTiming);
   if (e != cudaSuccess) return lrbms_fail(ctx, LRBMS_ERR_CUDA, std::string("band solver: ") + cudaGetErrorString(e));
   return LRBMS_OK;
+}
+
+void lrbms_band_release(lrbms_band_plan& B) {
+  if (B.ev_diag) cudaEventDestroy(B.ev_diag);
+  if (B.ev_potrf) cudaEventDestroy(B.ev_potrf);
+  if (B.side) cudaStreamDestroy(B.side);
+  B.ev_diag = B.ev_potrf = nullptr;
+  B.side = nullptr;
 }
 
 int64_t lrbms_band_chunk(const lrbms_band_plan& B, int64_t n_mu, size_t workspace_bytes) {
@@ -488,8 +499,15 @@ int lrbms_band_solve(lrbms_context* ctx, const lrbms_band_plan& B, int64_t n_mu,
     const double* th = theta + lo * n_theta;
     for (int J = 0; J < B.nbc; ++J) {
       const int n_t = std::min(B.kb, B.nbc - 1 - J) + 1;
-      band_update_kernel<<<dim3((unsigned)n_t, (unsigned)m), kUpdThreads, B.upd_smem, s>>>(P, J, th, work);
-      band_potrf_kernel<<<(unsigned)m, 256, B.potrf_smem, s>>>(P, J, work, info ? info + lo : nullptr);
+      // look-ahead: the diagonal target and its factorisation (one latency-bound CTA per parameter) run on the side stream
+      // beside the off-diagonal updates of the column, which do not need them; the triangular solves wait for both
+      cudaEventRecord(B.ev_diag, s);                       // everything up to the triangular solves of column J - 1
+      cudaStreamWaitEvent(B.side, B.ev_diag, 0);
+      band_update_kernel<<<dim3(1, (unsigned)m), kUpdThreads, B.upd_smem, B.side>>>(P, J, 0, th, work);
+      band_potrf_kernel<<<(unsigned)m, 256, B.potrf_smem, B.side>>>(P, J, work, info ? info + lo : nullptr);
+      cudaEventRecord(B.ev_potrf, B.side);
+      if (n_t > 1) band_update_kernel<<<dim3((unsigned)(n_t - 1), (unsigned)m), kUpdThreads, B.upd_smem, s>>>(P, J, 1, th, work);
+      cudaStreamWaitEvent(s, B.ev_potrf, 0);
       if (n_t > 1) band_trsm_kernel<<<dim3((unsigned)(n_t - 1), (unsigned)m), kUpdThreads, B.trsm_smem, s>>>(P, J, work);
     }
     band_substitute_kernel<<<(unsigned)m, 256, 0, s>>>(P, th, work, u + lo * B.n_red);

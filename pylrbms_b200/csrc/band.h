@@ -14,7 +14,11 @@ struct lrbms_band_plan {
   const double* d_rhs = nullptr;
   double flops_per_mu = 0;
   size_t upd_smem = 0, trsm_smem = 0, potrf_smem = 0;
+  // look-ahead: the diagonal block's factorisation runs on a side stream beside the off-diagonal updates of its column
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_diag = nullptr, ev_potrf = nullptr;
 };
+void lrbms_band_release(lrbms_band_plan& B);
 
 // host_blocks: the packed reduced blocks (host copy); host_rhs: [Qf][n_red]
 int lrbms_band_build(lrbms_plan* plan, lrbms_band_plan& B, int32_t n_sub, const int32_t* sizes, const int32_t* offsets, int32_t Q,

@@ -1026,6 +1026,7 @@ struct OnlinePlan : lrbms_plan {
   int est_tmu = kTMUMax;        // parameters per estimator CTA
   bool has_estimator = false;
   int run(void*) override { return lrbms_fail(ctx, LRBMS_ERR_INVALID, "online plans are run with lrbms_online_*"); }
+  ~OnlinePlan() override { lrbms_band_release(band); }
 };
 
 }  // namespace
@@ -1297,7 +1298,7 @@ int lrbms_online_plan_create(lrbms_handle_t h, const lrbms_reduced_system_t* sys
   }
 #undef UP_I32
 #undef UP_F64
-  P->info_launches = P->use_band ? 3.0 * P->band.nbc + 4 : 3;
+  P->info_launches = P->use_band ? 4.0 * P->band.nbc + 4 : 3;
   P->info_ctas = P->solve_grid;
   // introspection (lrbms_plan_info 6 .. 9): which solve kernel the plan selected, executed factor flops per parameter
   // (the 8x8-tile count for the CTA-per-parameter kernels, the dense-band count of the band solver), half bandwidth

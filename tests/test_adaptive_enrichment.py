@@ -7,7 +7,7 @@ tests compare the PCG neighbourhood solve with a sparse direct solve and the who
 import numpy as np
 import pytest
 
-ETA_TOL = 1e-9
+ETA_TOL = 1e-10
 
 
 def _brute_force_doerfler(indicators, theta):
