@@ -224,11 +224,13 @@ typedef struct {
   int64_t matrix_offset;   /* into the estimator matrix buffer, in doubles; M row-major, ld = cols */
 } lrbms_estimator_term_t;
 
-/* Solve kernel of an online plan.  AUTO: the shared-memory-window kernel (one SM per parameter, live factor window in
- * shared memory) when the window fits, else the block-banded out-of-HBM Cholesky (whole GPU per chunk of parameters).
+/* Solve kernel of an online plan.  AUTO: a shared-memory-window kernel (one SM per parameter, live factor window in
+ * shared memory) when the window fits -- PANEL (two tile columns per pipeline stage, 2 x 2 register-blocked updates) when its
+ * schedule applies, else WINDOW (one column per stage) -- else the block-banded out-of-HBM Cholesky (whole GPU per chunk).
  * WINDOW / BANDED force one of them (WINDOW fails with LRBMS_ERR_UNSUPPORTED when the window does not fit);
  * GLOBAL_TILES is the first-generation kernel (tile factor in global scratch), kept for cross-checks. */
-enum { LRBMS_SOLVER_AUTO = 0, LRBMS_SOLVER_WINDOW = 1, LRBMS_SOLVER_GLOBAL_TILES = 2, LRBMS_SOLVER_BANDED = 3 };
+enum { LRBMS_SOLVER_AUTO = 0, LRBMS_SOLVER_WINDOW = 1, LRBMS_SOLVER_GLOBAL_TILES = 2, LRBMS_SOLVER_BANDED = 3,
+       LRBMS_SOLVER_PANEL = 4 };
 
 typedef struct {
   int32_t n_sub;

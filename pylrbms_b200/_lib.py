@@ -29,8 +29,8 @@ EXPORTS = [
 
 VEC_ONE, VEC_UI, VEC_UN, VEC_UR = 0, 1, 2, 3
 OUT_NC, OUT_R, OUT_DF = 0, 1, 2
-SOLVER_AUTO, SOLVER_WINDOW, SOLVER_GLOBAL_TILES, SOLVER_BANDED = 0, 1, 2, 3
-SOLVER_NAMES = {1: 'solve_kernel_v2', 2: 'solve_kernel', 3: 'band_update_kernel'}
+SOLVER_AUTO, SOLVER_WINDOW, SOLVER_GLOBAL_TILES, SOLVER_BANDED, SOLVER_PANEL = 0, 1, 2, 3, 4
+SOLVER_NAMES = {1: 'solve_kernel_v2', 2: 'solve_kernel', 3: 'band_update_kernel', 4: 'solve_kernel_v3'}
 
 
 class LrbmsError(RuntimeError):

@@ -17,6 +17,7 @@
 
 #include "band.h"
 #include "common.cuh"
+#include "online3.h"
 #include "symbolic.h"
 
 namespace {
@@ -1017,6 +1018,10 @@ struct OnlinePlan : lrbms_plan {
   bool use_v2 = false;
   bool use_band = false;        // block-banded out-of-HBM Cholesky (band.cu): systems whose factor window exceeds one SM
   lrbms_band_plan band;
+  bool use_v3 = false;          // two-column panel kernel (online3.cu)
+  lrbms_symbolic3 sym3;
+  V3Params v3;
+  size_t v3_smem = 0;
   size_t solve2_smem = 0;
   int64_t solve_stride = 0;     // doubles of factor scratch per resident CTA of the selected solve kernel
   EstParams ep;
@@ -1042,13 +1047,13 @@ int lrbms_online_plan_create(lrbms_handle_t h, const lrbms_reduced_system_t* sys
   P->ctx = h;
   P->kind = PLAN_ONLINE;
   std::string err;
-  LRBMS_REQUIRE(h, sys->solver >= LRBMS_SOLVER_AUTO && sys->solver <= LRBMS_SOLVER_BANDED, "online_plan_create: unknown solver");
+  LRBMS_REQUIRE(h, sys->solver >= LRBMS_SOLVER_AUTO && sys->solver <= LRBMS_SOLVER_PANEL, "online_plan_create: unknown solver");
   int rc = lrbms_symbolic_basics(P->sym, sys->n_sub, sys->basis_sizes, sys->n_blocks, sys->block_i, sys->block_j, &err);
   if (rc) { delete P; return lrbms_fail(h, rc, err); }
   // The 8x8-tile schedule is only built when a CTA-per-parameter kernel can use it: its pair lists grow like
   // n (b / 8)^2 / 2 (135 M pairs for the 8x8x8, N = 40 system), the band solver needs none of it.
   const double est_pairs = 0.5 * P->sym.ntc * (P->sym.half_bandwidth / 8.0 + 1.0) * (P->sym.half_bandwidth / 8.0 + 1.0);
-  bool tiles_built = sys->solver == LRBMS_SOLVER_WINDOW || sys->solver == LRBMS_SOLVER_GLOBAL_TILES ||
+  bool tiles_built = sys->solver == LRBMS_SOLVER_WINDOW || sys->solver == LRBMS_SOLVER_GLOBAL_TILES || sys->solver == LRBMS_SOLVER_PANEL ||
                (sys->solver == LRBMS_SOLVER_AUTO && est_pairs <= 3.0e7);
   if (tiles_built) {
     rc = lrbms_symbolic_build(P->sym, sys->n_sub, sys->basis_sizes, sys->n_blocks, sys->block_i, sys->block_j, &err);
@@ -1142,8 +1147,72 @@ int lrbms_online_plan_create(lrbms_handle_t h, const lrbms_reduced_system_t* sys
     P->solve_grid = per_sm * h->sm_count;
   }
   P->solve_stride = sp.work_stride;
+  // ---- two-column panel kernel (v3): on request only -- measured slower than the one-column kernel (profiles/README.md:
+  //      bound by warp 0's critical chain of two 8x8 Cholesky + inverses per panel), kept with its CPU-emulated schedule
+  if (sys->solver == LRBMS_SOLVER_PANEL) {
+    rc = lrbms_symbolic3_build(P->sym3, S);
+    if (rc) { lrbms_plan_destroy(P); return rc; }
+    const lrbms_symbolic3& S3 = P->sym3;
+    if (S3.ok) {
+      V3Params& v = P->v3;
+      int max_col = 1;
+      std::vector<int32_t> ccol(4 * (size_t)S3.ntc, 0);
+      for (int J = 0; J < S3.ntc; ++J) {
+        const int32_t c0 = S3.col_ptr[J], nc = S3.col_ptr[J + 1] - c0;
+        ccol[4 * J] = c0; ccol[4 * J + 1] = nc;
+        ccol[4 * J + 3] = (nc >= 2 && S3.row_idx[c0 + 1] == J + 1) ? 1 : 0;
+        max_col = std::max(max_col, nc);
+      }
+      v.n_red = S.n_red; v.n_pad = S.n_pad; v.ntc = S3.ntc; v.np = S3.np; v.Q = Q; v.Qf = Qf; v.n_theta = Q + Qf;
+      v.n_a_tiles = S.n_a_tiles; v.n_win = S3.n_win_slots; v.acc_rows = S3.acc_rows; v.n_partial = std::max(1, S3.n_partial);
+      v.max_col = max_col;
+      v.max_steps = std::max(1, S3.max_steps);
+      v.back_stage_doubles = max_col * 64;
+      v.region_doubles = std::max((S3.n_win_slots + 1) * 64, lrbms_v3_back_stages() * max_col * 64);
+      v.work_stride = S3.n_tiles() * 64;
+      v.a_tiles = sp.a_tiles; v.rhs = sp.rhs;
+      v.timing = nullptr;
+#ifdef LRBMS_DEVTOOLS
+      if (const char* tenv = getenv("LRBMS_SOLVE_TIMING")) {
+        if (atoi(tenv) > 0) {
+          rc = plan_alloc(P, &v.timing, (size_t)kV3Warps * 8);
+          if (rc) { lrbms_plan_destroy(P); return rc; }
+          PLAN_CUDA_CHECK(cudaMemset(v.timing, 0, sizeof(long long) * kV3Warps * 8));
+        }
+      }
+#endif
+      size_t smem3 = 0;
+      rc = lrbms_v3_prepare(h, v, &smem3);
+      if (rc == LRBMS_OK) {
+        std::vector<int32_t> steps = S3.steps;
+        if (steps.empty()) steps.assign(4, 0);
+        V3Own* d_own = nullptr; V3Panel* d_pan = nullptr;
+        rc = plan_upload(P, &d_own, S3.own);
+        if (!rc) rc = plan_upload(P, &d_pan, S3.pan);
+        if (rc) { lrbms_plan_destroy(P); return rc; }
+        v.own = d_own; v.pan = d_pan;
+        const int32_t* tmp = nullptr;
+        UP_I32(tmp, steps); v.steps = reinterpret_cast<const int4*>(tmp);
+        UP_I32(tmp, ccol);  v.ccol = reinterpret_cast<const int4*>(tmp);
+        UP_I32(v.row_idx, S3.row_idx);
+        P->v3_smem = smem3;
+        P->use_v3 = true;
+        P->solve_grid = h->sm_count;
+        P->solve_stride = v.work_stride;
+      } else if (rc != LRBMS_ERR_UNSUPPORTED) {
+        lrbms_plan_destroy(P);
+        return rc;
+      }
+    }
+  }
+  if (sys->solver == LRBMS_SOLVER_PANEL && !P->use_v3) {
+    const std::string why = "online_plan_create: the panel kernel does not apply (" +
+                            (P->sym3.why.empty() ? std::string("window does not fit") : P->sym3.why) + ")";
+    lrbms_plan_destroy(P);
+    return lrbms_fail(h, LRBMS_ERR_UNSUPPORTED, why);
+  }
   // ---- shared-memory-window kernel (v2): used whenever the live window of L fits into shared memory
-  {
+  if (!P->use_v3) {
     const int maxcol = std::max(1, S.max_targets - 1);
     const int MT = S.max_targets;
     const int64_t region = std::max<int64_t>((int64_t)S.n_win_slots * 64, (int64_t)kBackStages * maxcol * 64);
@@ -1156,7 +1225,7 @@ int lrbms_online_plan_create(lrbms_handle_t h, const lrbms_reduced_system_t* sys
     PLAN_CUDA_CHECK(cudaFuncGetAttributes(&fa2, solve_kernel_v2));
     // the static shared memory of the kernel (mbarriers, status word) counts against the same per-block limit
     if (bytes + fa2.sharedSizeBytes <= (size_t)h->max_smem_optin && sys->solver != LRBMS_SOLVER_GLOBAL_TILES &&
-        sys->solver != LRBMS_SOLVER_BANDED) {
+        sys->solver != LRBMS_SOLVER_BANDED && sys->solver != LRBMS_SOLVER_PANEL) {
       SolveParamsV2& s2 = P->sp2;
       s2.base = sp;
       s2.base.work_stride = (int64_t)S.n_tiles() * 64;
@@ -1201,7 +1270,7 @@ int lrbms_online_plan_create(lrbms_handle_t h, const lrbms_reduced_system_t* sys
     return lrbms_fail(h, LRBMS_ERR_UNSUPPORTED, "online_plan_create: the live factor window does not fit the shared memory of one SM");
   }
   // ---- band solver (band.cu): everything the CTA-per-parameter window kernel cannot hold
-  if (!P->use_v2 && sys->solver != LRBMS_SOLVER_GLOBAL_TILES) {
+  if (!P->use_v2 && !P->use_v3 && sys->solver != LRBMS_SOLVER_GLOBAL_TILES) {
     rc = lrbms_band_build(P, P->band, S.n_sub, S.sizes.data(), S.offsets.data(), Q, Qf, sys->n_blocks, sys->block_i, sys->block_j,
                           sys->block_offset, hb.data(), tmp.data());
     if (rc) { lrbms_plan_destroy(P); return rc; }
@@ -1302,8 +1371,8 @@ int lrbms_online_plan_create(lrbms_handle_t h, const lrbms_reduced_system_t* sys
   P->info_ctas = P->solve_grid;
   // introspection (lrbms_plan_info 6 .. 9): which solve kernel the plan selected, executed factor flops per parameter
   // (the 8x8-tile count for the CTA-per-parameter kernels, the dense-band count of the band solver), half bandwidth
-  P->info_solver = P->use_v2 ? LRBMS_SOLVER_WINDOW : P->use_band ? LRBMS_SOLVER_BANDED : LRBMS_SOLVER_GLOBAL_TILES;
-  P->info_solve_flops = P->use_band ? P->band.flops_per_mu : (double)S.flops;
+  P->info_solver = P->use_v3 ? LRBMS_SOLVER_PANEL : P->use_v2 ? LRBMS_SOLVER_WINDOW : P->use_band ? LRBMS_SOLVER_BANDED : LRBMS_SOLVER_GLOBAL_TILES;
+  P->info_solve_flops = P->use_band ? P->band.flops_per_mu : P->use_v3 ? (double)P->sym3.flops : (double)S.flops;
   P->info_half_bandwidth = S.half_bandwidth;
   // uploads and clears above ran on the legacy default stream: finish them before a caller's non-blocking stream runs the plan
   PLAN_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)0));
@@ -1342,7 +1411,9 @@ int lrbms_online_solve(lrbms_plan_t plan, int64_t n_mu, const double* theta, dou
   }
   LRBMS_REQUIRE(P->ctx, workspace_bytes >= solve_ws_bytes(P, n_mu), "online_solve: workspace too small (see lrbms_online_workspace_bytes)");
   const int grid = (int)std::min<int64_t>(P->solve_grid, n_mu);
-  if (P->use_v2)
+  if (P->use_v3)
+    lrbms_v3_launch(P->v3, grid, P->v3_smem, n_mu, theta, u, info, (double*)workspace, (cudaStream_t)stream);
+  else if (P->use_v2)
     solve_kernel_v2<<<grid, kV2Threads, P->solve2_smem, (cudaStream_t)stream>>>(P->sp2, n_mu, theta, u, info, (double*)workspace);
   else
     solve_kernel<<<grid, kSolveThreads, P->solve_smem, (cudaStream_t)stream>>>(P->sp, n_mu, theta, u, info, (double*)workspace);
@@ -1386,9 +1457,10 @@ int lrbms_online_debug_timing(lrbms_plan_t plan, int64_t* out_host, int32_t n) {
   if (!plan || plan->kind != PLAN_ONLINE || !out_host) return LRBMS_ERR_INVALID;
   OnlinePlan* P = static_cast<OnlinePlan*>(plan);
 #ifdef LRBMS_DEVTOOLS
-  if (!P->use_v2 || !P->sp2.timing) return lrbms_fail(P->ctx, LRBMS_ERR_INVALID, "debug timing is off (set LRBMS_SOLVE_TIMING=1 before creating the plan)");
+  long long* src = P->use_v3 ? P->v3.timing : (P->use_v2 ? P->sp2.timing : nullptr);
+  if (!src) return lrbms_fail(P->ctx, LRBMS_ERR_INVALID, "debug timing is off (set LRBMS_SOLVE_TIMING=1 before creating the plan)");
   const int cnt = std::min<int>(n, kV2Warps * 8);
-  LRBMS_CUDA_CHECK(P->ctx, cudaMemcpy(out_host, P->sp2.timing, sizeof(long long) * cnt, cudaMemcpyDeviceToHost));
+  LRBMS_CUDA_CHECK(P->ctx, cudaMemcpy(out_host, src, sizeof(long long) * cnt, cudaMemcpyDeviceToHost));
   return cnt;
 #else
   (void)n;

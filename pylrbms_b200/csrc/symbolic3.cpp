@@ -103,6 +103,7 @@ int lrbms_symbolic3_build(lrbms_symbolic3& S3, const lrbms_symbolic& S) {
     for (int k = 0; k < kV3MaxFold; ++k) P.fold[k] = -1;
     P.head_prev = p > 0;
     P.acc_rows[0] = acc_of(P.c0); P.acc_rows[1] = acc_of(P.c1);
+    P.step0 = P.n_steps = 0; P.pad[0] = P.pad[1] = 0;
     for (int r = 0; r < 2; ++r) {
       const int I = 2 * p + r;
       P.head_exists[r] = p > 0 && std::binary_search(rows[p - 1].begin(), rows[p - 1].end(), I);
@@ -151,8 +152,14 @@ int lrbms_symbolic3_build(lrbms_symbolic3& S3, const lrbms_symbolic& S) {
         }
       }
     }
-    if (q == np) continue;
+    if (q == np) {               // only the forward-substitution block: its rows of panel np - 1 are solved, nothing is updated
+      V3Own& o = S3.own[(size_t)q * kV3Warps + 1 + n_blocks];
+      o.chunk_step[0] = 0; o.chunk_n[0] = 0; o.chunk_dest[0] = -1; o.chunk_kind[0] = 1;
+      o.n_chunks = 1;
+      continue;
+    }
     // --- early-update steps: sources K < 2 p (every column before panel p)
+    S3.pan[q].step0 = (int32_t)(S3.steps.size() / 4);
     std::vector<std::vector<int32_t>> bsteps(n_blocks + 2);     // [0 .. n_blocks - 1] tile blocks, [n_blocks] rhs, [n_blocks + 1] diagonal
     for (int K = 0; K < 2 * p; ++K) {
       const int32_t b0 = wslot(t0, K), b1 = wslot(t1, K);
@@ -198,6 +205,8 @@ int lrbms_symbolic3_build(lrbms_symbolic3& S3, const lrbms_symbolic& S) {
         o.n_chunks = 1;
       }
     }
+    S3.pan[q].n_steps = (int32_t)(S3.steps.size() / 4) - S3.pan[q].step0;
+    S3.max_steps = std::max(S3.max_steps, S3.pan[q].n_steps);
     // longest helper chunks first, each to the least loaded update warp
     std::stable_sort(helpers.begin(), helpers.end(), [](const Chunk& a, const Chunk& b) { return a.n * (a.kind ? 1 : 2) > b.n * (b.kind ? 1 : 2); });
     int n_part = 0;
@@ -263,6 +272,7 @@ int lrbms_symbolic3_info(lrbms_symbolic3_t s, int32_t what, int64_t* out) {
     case 8: *out = (int64_t)(sizeof(V3Panel) / 4); break;
     case 9: *out = (int64_t)(s->steps.size() / 4); break;
     case 10: *out = (int64_t)s->why.size(); break;
+    case 11: *out = s->max_steps; break;
     default: return LRBMS_ERR_INVALID;
   }
   return LRBMS_OK;

@@ -29,6 +29,7 @@ struct V3Own {
   int32_t chunk_n[kV3MaxChunks];      // steps in the chunk
   int32_t chunk_dest[kV3MaxChunks];   // -1: this warp's own block (kept in registers); >= 0: partial-buffer block
   int32_t chunk_kind[kV3MaxChunks];   // 0: tile block (4 operand slots per step); 1: right-hand-side block
+  int32_t pad;                        // record size: 44 words = 176 bytes (16-byte multiples for the staging copies)
 };
 
 // per panel p: the diagonal block and the head rows (what the chain warp handles)
@@ -45,6 +46,8 @@ struct V3Panel {
   int32_t head_w[2][2];        // window slots of (c0, c0p), (c0, c1p), (c1, c0p), (c1, c1p)
   int32_t head_g[2][2];        // factor slots of the same
   int32_t acc_rows[2];         // accumulator rows of c0, c1 as diagonal rows (where the diagonal block lives)
+  int32_t step0, n_steps;      // the early-update steps of this panel's blocks: steps[step0 .. step0 + n_steps)
+  int32_t pad[2];              // record size: 32 words = 128 bytes (16-byte multiples for the staging copies)
 };
 
 struct lrbms_symbolic3 {
@@ -56,6 +59,7 @@ struct lrbms_symbolic3 {
   int32_t n_win_slots = 0;     // live window tiles (peak); slot n_win_slots is an all-zero tile
   int32_t acc_rows = 0;        // rows of the accumulator ring
   int32_t n_partial = 0;       // partial blocks (peak per panel)
+  int32_t max_steps = 0;       // early-update steps of one panel (peak)
   std::vector<V3Own> own;      // [(np + 1) * kV3Warps]
   std::vector<V3Panel> pan;    // [np]
   std::vector<int32_t> steps;  // 4 int32 per step: a0, a1, b0, b1 (window slots; right-hand-side block: K, unused, b0, b1)

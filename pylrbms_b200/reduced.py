@@ -342,7 +342,7 @@ class ReducedModel:
         sysc.n_blocks, sysc.block_i, sysc.block_j, sysc.block_offset = len(pattern), bi.ctypes.data, bj.ctypes.data, boff.ctypes.data
         sysc.lhs_blocks, sysc.rhs = buf.data_ptr(), rhs.data_ptr()
         sysc.solver = {'auto': L.SOLVER_AUTO, 'window': L.SOLVER_WINDOW, 'global_tiles': L.SOLVER_GLOBAL_TILES,
-                       'banded': L.SOLVER_BANDED}[self.solver]
+                       'banded': L.SOLVER_BANDED, 'panel': L.SOLVER_PANEL}[self.solver]
         keep = [bi, bj, boff, sizes, rhs, buf]
         has_est = self.estimator is not None and all('nc_{}'.format(s) in self.operators for s in self.estimator.subdomains)
         if has_est:

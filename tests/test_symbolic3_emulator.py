@@ -70,6 +70,7 @@ def _pan(rec):
     P['head_w'] = [take(2), take(2)]
     P['head_g'] = [take(2), take(2)]
     P['acc_rows'] = take(2)
+    P['step0'], P['n_steps'], _ = take(3)
     return P
 
 

@@ -1,0 +1,9 @@
+set -x
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_kernels.py -m gpu -q -x -k "solve_matches_dense or reproducible" > gpurun_out/r02i_pytest.log 2>&1; echo "pytest rc=$?"
+tail -15 gpurun_out/r02i_pytest.log
+python bench.py --steps 3 --warmup 3 --no-offline --no-cpu-baseline --no-c5 > gpurun_out/r02i_bench.json 2> gpurun_out/r02i_bench.err; echo "bench rc=$?"; tail -c 600 gpurun_out/r02i_bench.err
+python -c "
+import json
+d=json.load(open('gpurun_out/r02i_bench.json')); r=d['roofline']; print(d['value'], d['e2e']['value'], r['kernel'], r['ms_per_launch'], r['frac'], r['executed_frac'], d.get('parity',{}).get('max_rel'))
+"
