@@ -50,7 +50,9 @@ __device__ __forceinline__ double* band_block(double* base, const BandParams& P,
 //  T_IJ = A_IJ(mu) - sum_{K = max(0, I - kb)}^{J - 1} L_IK L_JK^T          grid: (kb + 1 targets, parameters)
 //  8 warps as 4 (rows) x 2 (columns): a warp owns 16 x 32 of the target = 2 x 4 DMMA tiles.
 // ------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kUpdThreads, 2)
+// 112 registers: two CTAs of this kernel leave register room for a CTA of band_potrf_kernel on the same SM, so that the
+// look-ahead factorisation of the diagonal block really runs beside the off-diagonal updates
+__global__ void __maxnreg__(112)
 band_update_kernel(BandParams P, int J, int d0, const double* __restrict__ theta, double* __restrict__ work) {
   extern __shared__ __align__(128) double smem[];
   __shared__ __align__(8) unsigned long long full_bar[kUpdStages];
@@ -143,8 +145,11 @@ constexpr int kPotrfLd = NB + 1;
 __global__ void __launch_bounds__(256)
 band_potrf_kernel(BandParams P, int J, double* __restrict__ work, int32_t* __restrict__ info) {
   extern __shared__ __align__(128) double smem[];
-  double* S = smem;                       // the diagonal block, row-major; the factor overwrites its lower triangle
-  double* Wt = smem + NB * kPotrfLd;      // Wt[j][i] = W[i][j]: column j of the inverse, contiguous for its owner threads
+  double* S = smem;                       // the diagonal block, row-major; the factor overwrites its lower triangle and the
+                                          // inverse W = L^-1 goes, transposed, into the (unused) strictly upper triangle:
+                                          // W[i][j] (i > j) at S[j][i] -- one 33 KB buffer, so that a CTA of this kernel
+                                          // fits beside two CTAs of band_update_kernel on one SM (look-ahead)
+  __shared__ double wd[NB];               // diagonal of W
   __shared__ int s_bad;
   const int64_t mu = blockIdx.x;
   double* base = work + mu * P.per_mu;
@@ -175,19 +180,20 @@ band_potrf_kernel(BandParams P, int J, double* __restrict__ work, int32_t* __res
       const double li = S[row * kPotrfLd + k];
       for (int j = k + 1 + part; j <= row; j += 4) S[row * kPotrfLd + j] -= li * S[j * kPotrfLd + k];
     }
-    // (the next iteration's first barrier orders these updates before anybody overwrites column k + 1)
     __syncthreads();
   }
   // inverse: four threads per column j of W, forward substitution  W[i][j] = (delta_ij - sum_{k<i} L[i][k] W[k][j]) / L[i][i]
   {
     const int j = tid >> 2, p4 = tid & 3;
-    double* wj = Wt + j * kPotrfLd;
-    for (int i = 0; i < NB; ++i) {
+    double* wj = S + j * kPotrfLd;                            // W[k][j], k > j, at wj[k] (upper triangle, row j)
+    if (p4 == 0) wd[j] = 1.0 / S[j * kPotrfLd + j];
+    __syncwarp();
+    for (int i = 1; i < NB; ++i) {                            // uniform trip count: the shuffles are warp-wide
       double s = 0.0;
-      for (int k = j + p4; k < i; k += 4) s += S[i * kPotrfLd + k] * wj[k];
+      for (int k = j + p4; k < i; k += 4) s += S[i * kPotrfLd + k] * ((k == j) ? wd[j] : wj[k]);
       s += __shfl_xor_sync(0xffffffffu, s, 1);
       s += __shfl_xor_sync(0xffffffffu, s, 2);
-      if (p4 == 0) wj[i] = (i < j) ? 0.0 : (((i == j) ? 1.0 : 0.0) - s) / S[i * kPotrfLd + i];
+      if (p4 == 0 && i > j) wj[i] = -s / S[i * kPotrfLd + i];
       __syncwarp();
     }
   }
@@ -195,7 +201,8 @@ band_potrf_kernel(BandParams P, int J, double* __restrict__ work, int32_t* __res
   double* W = base + P.winv_off + (int64_t)J * kBlk;
   for (int e = tid; e < kBlk; e += 256) {
     const int t = e & 3, g = (e >> 2) & 7, rt = (e >> 5) & 7, ks = e >> 8;
-    W[e] = Wt[(4 * ks + t) * kPotrfLd + 8 * rt + g];          // W[r][c] with r = 8 rt + g, c = 4 ks + t
+    const int r = 8 * rt + g, c = 4 * ks + t;                 // W[r][c]
+    W[e] = (r == c) ? wd[r] : (r > c ? S[c * kPotrfLd + r] : 0.0);
   }
   if (tid == 0 && s_bad && info && info[mu] == 0) info[mu] = s_bad;
 }
@@ -451,7 +458,7 @@ int lrbms_band_build(lrbms_plan* plan, lrbms_band_plan& B, int32_t n_sub, const 
   B.flops_per_mu = fl;
   B.upd_smem = sizeof(double) * kUpdStages * 2 * kChunkDoubles;
   B.trsm_smem = sizeof(double) * 2 * kBlk;
-  B.potrf_smem = sizeof(double) * 2 * NB * kPotrfLd;
+  B.potrf_smem = sizeof(double) * NB * kPotrfLd;
   cudaError_t e = cudaFuncSetAttribute(band_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B.upd_smem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(band_potrf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B.potrf_smem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(band_trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B.trsm_smem);
