@@ -4,7 +4,7 @@
 
 constexpr int kBandNB = 64;                       // block size (8 x 8 DMMA tiles)
 constexpr int kBandMaxKb = 63;                    // block half bandwidth supported by the substitution kernel's ring
-constexpr size_t kBandWorkspaceBudget = (size_t)24 << 30;   // default factor workspace per chunk of parameters
+constexpr size_t kBandWorkspaceBudget = (size_t)32 << 30;   // default factor workspace per chunk of parameters (C4: all 64 in one)
 
 struct lrbms_band_plan {
   int32_t n_red = 0, n_pad = 0, nbc = 0, kb = 0, Q = 0, Qf = 0, n_a = 0, half_bandwidth = 0;

@@ -367,7 +367,9 @@ solve_kernel_v2(SolveParamsV2 P2, int64_t n_mu, const double* __restrict__ theta
 #ifdef LRBMS_DEVTOOLS
   const bool timing = P2.timing != nullptr && blockIdx.x == 0;
   long long tph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tlast = 0;
-#define LRBMS_TICK(k) do { if (timing) { const long long now_ = clock64(); tph[k] += now_ - tlast; tlast = now_; } } while (0)
+// (bar.sync compiles to BAR.SYNC.DEFER_BLOCKING: a clock read right behind it is taken before the wait; the volatile
+// shared-memory read makes the barrier complete first)
+#define LRBMS_TICK(k) do { if (timing) { const int dummy_ = *(volatile int*)&s_info; const long long now_ = clock64() + (dummy_ & 0); tph[k] += now_ - tlast; tlast = now_; } } while (0)
 #else
 #define LRBMS_TICK(k) do { } while (0)
 #endif
