@@ -153,3 +153,23 @@ def test_reduced_operator_is_spd_and_solution_satisfies_system():
         U = rd.solve(mu)
         f = rd.rhs.as_source_array(rd.parse_parameter(mu)).data[0]
         assert np.abs(A @ U.data[0] - f).max() <= 1e-12 * np.abs(f).max()
+
+
+def test_parity_checker_scales_bound_the_forms():
+    """``oracle/parity.py``: the summed-magnitude scales ``S`` the parity criterion uses must bound the estimator parts they
+    belong to (|x^T M y| <= |x|^T |M| |y| term by term), and comparing the oracle with itself must give exact zeros."""
+    from pylrbms_b200.swipdg_fixture import assemble_block_swipdg, make_local_bases
+    from oracle import lrbms_oracle as O
+    from oracle.parity import ULPS, reference_online
+    data = assemble_block_swipdg((3, 2), 4)
+    bases = make_local_bases(data, [3, 5, 4, 6, 5, 4], seed=2)
+    rd_ref = O.LRBMSReductor(O.build_discretization(data), bases={'domain_%d' % i: bases[i] for i in range(6)}).reduce()
+    mus = [0.15, 0.6, 1.0]
+    U, eta, parts, ind, As, S, consts = reference_online(rd_ref, mus)
+    assert S.shape == parts.shape == (3, 6, 3)
+    assert np.all(S >= np.abs(parts) * (1 - 1e-12))
+    assert np.all(consts > 0) and 0 < ULPS < 1e-3
+    # the scale of eta bounds eta itself
+    a_bar, g_bar, a_hat = consts[:, 0], consts[:, 1], consts[:, 2]
+    s_eta = (np.sqrt(g_bar) * np.linalg.norm(S[0], axis=0) + np.linalg.norm(S[1] + S[2], axis=0) / np.sqrt(a_hat)) / np.sqrt(a_bar)
+    assert np.all(s_eta >= eta * (1 - 1e-12))
