@@ -24,10 +24,11 @@ CMD2="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-offline --no-p
 $CMD2 > $O/${TAG}_plain3.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:"solve_kernel_v2|estimate_kernel" -s 6 -c 2 -f -o $O/${TAG}_online $CMD2 > $O/${TAG}_ncu_online.log 2>&1
 echo "online rc=$?"
-# ... and the band solver at the 8x8x8, N = 40 size (block column 160 of 320: full-length updates)
+# ... and the band solver at the 8x8x8, N = 40 size (block column 160 of 320: full-length updates; two update launches per
+# column: the off-diagonal targets on the main stream, the diagonal target on the side stream)
 CMD3="python bench.py --config c4 --steps 1 --warmup 3 --no-cpu-baseline --no-offline"
 $CMD3 > $O/${TAG}_plain4.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:"band_update_kernel" -s 480 -c 1 -f -o $O/${TAG}_band_update $CMD3 > $O/${TAG}_ncu_band.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"band_update_kernel" -s 321 -c 2 -f -o $O/${TAG}_band_update $CMD3 > $O/${TAG}_ncu_band.log 2>&1
 echo "band rc=$?"
 ncu --set full --clock-control none --import-source on -k regex:"band_potrf_kernel|band_trsm_kernel|band_substitute_kernel" -s 320 -c 2 -f -o $O/${TAG}_band_rest $CMD3 > $O/${TAG}_ncu_band2.log 2>&1
 echo "band2 rc=$?"
