@@ -462,7 +462,7 @@ def measure_offline(a, torch, planner, d, bases, fp64_peak, flush_l2, t_reduce_f
 
 def measure_sharded_offline(a, torch, dist, d, bases, flush_l2, barrier, ms_unsharded, label):
     """Strong scaling of the offline half: the same operator set, subdomains split over the ranks, reduced regions exchanged
-    by one in-place all-gather.  The gathered buffer must equal the unsharded result bit for bit (checked here)."""
+    over peer memory (NCCL all-gather timed beside it).  The gathered buffer must equal the unsharded result bit for bit (checked here)."""
     from pylrbms_b200 import LRBMSReductor
     world = dist.get_world_size()
     red_s = LRBMSReductor(d, bases=bases, shard=True)
@@ -482,7 +482,20 @@ def measure_sharded_offline(a, torch, dist, d, bases, flush_l2, barrier, ms_unsh
         e2.record()
         e2.synchronize()
         t_run.append(e0.elapsed_time(e1)); t_all.append(e0.elapsed_time(e2))
-    tt = torch.tensor([float(np.mean(t_run)), float(np.mean(t_all))], dtype=torch.float64, device='cuda')
+    # the same exchange through NCCL (one in-place all-gather), timed beside the peer-memory path
+    from pylrbms_b200.distributed import exchange_kind, exchange_regions
+    t_nccl = []
+    for it in range(3 + max(3, a.steps)):
+        flush_l2()
+        barrier()
+        e0, e1 = (torch.cuda.Event(enable_timing=True) for _ in range(2))
+        e0.record()
+        exchange_regions(ps.out, ps.region_starts)
+        e1.record()
+        e1.synchronize()
+        if it >= 3:
+            t_nccl.append(e0.elapsed_time(e1))
+    tt = torch.tensor([float(np.mean(t_run)), float(np.mean(t_all)), float(np.mean(t_nccl))], dtype=torch.float64, device='cuda')
     dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     # bitwise check against the unsharded projection of the same bases on this rank
     red_u = LRBMSReductor(d, bases=bases)
@@ -503,7 +516,9 @@ def measure_sharded_offline(a, torch, dist, d, bases, flush_l2, barrier, ms_unsh
         'ms_all_stages_1gpu_unsharded_this_rank': ms_unsharded,
         'speedup_vs_unsharded': ms_unsharded / float(tt[0].item()),
         'speedup_vs_unsharded_incl_exchange': ms_unsharded / float(tt[1].item()),
-        'exchange': 'one in-place NCCL all-gather of equal-stride rank regions, %d doubles in total' % int(ps.out.numel()),
+        'exchange': '%s; equal-stride rank regions, %d doubles in total' % (exchange_kind(), int(ps.out.numel())),
+        'ms_exchange_max_over_ranks': float(tt[1].item()) - float(tt[0].item()),
+        'ms_exchange_nccl_all_gather_max_over_ranks': float(tt[2].item()),
         'bitwise_equal_to_unsharded': True,
         'projection_descriptors_this_rank': ps.n_project_descs,
     }

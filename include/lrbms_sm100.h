@@ -168,6 +168,15 @@ typedef struct {
 } lrbms_remap_desc_t;
 int lrbms_remap_blocks(lrbms_handle_t h, int32_t n, const lrbms_remap_desc_t* descs_host, void* stream);
 
+/* Multi-GPU exchange of the sharded offline results over peer memory (replaces the Allreduce(SUM) of zero-padded
+ * blocks at reference src/reductor.py:93).  Stores `n_bytes` at `src` (device, 16-byte aligned) to each of the `n_dst`
+ * device addresses in `dst_host` -- peer pointers of the other ranks' buffers mapped into this process (NVLink P2P), or,
+ * with multicast != 0, ONE NVSwitch multicast address (n_dst == 1) that the switch replicates to every GPU.  Stream
+ * ordered; the caller follows it with a cross-rank barrier (signal pads of the symmetric allocation) before reading. */
+#define LRBMS_MAX_PEERS 16
+int lrbms_peer_push(lrbms_handle_t h, const void* src, int64_t n_bytes, int32_t n_dst, const uint64_t* dst_host,
+                    int32_t multicast, void* stream);
+
 /* run / destroy / introspect any plan */
 int lrbms_plan_run(lrbms_plan_t plan, void* stream);
 int lrbms_plan_destroy(lrbms_plan_t plan);

@@ -24,7 +24,7 @@ EXPORTS = [
     'lrbms_symbolic3_create', 'lrbms_symbolic3_destroy', 'lrbms_symbolic3_info', 'lrbms_symbolic3_get',
     'lrbms_online_plan_create', 'lrbms_online_workspace_bytes', 'lrbms_online_solve', 'lrbms_online_estimate',
     'lrbms_online_sweep', 'lrbms_eta_max', 'lrbms_online_debug_timing',
-    'lrbms_pcg_workspace_bytes', 'lrbms_pcg_solve', 'lrbms_remap_blocks',
+    'lrbms_pcg_workspace_bytes', 'lrbms_pcg_solve', 'lrbms_remap_blocks', 'lrbms_peer_push',
 ]
 
 VEC_ONE, VEC_UI, VEC_UN, VEC_UR = 0, 1, 2, 3
@@ -129,6 +129,7 @@ def load_library():
             'lrbms_eta_max': (C.c_int, [vp, i64, vp, vp, vp, vp]),
             'lrbms_online_debug_timing': (C.c_int, [vp, vp, i32]),
             'lrbms_remap_blocks': (C.c_int, [vp, i32, vp, vp]),
+            'lrbms_peer_push': (C.c_int, [vp, vp, i64, i32, vp, i32, vp]),
             'lrbms_pcg_workspace_bytes': (C.c_int, [vp, i64, P(C.c_size_t)]),
             'lrbms_pcg_solve': (C.c_int, [vp, i32, vp, vp, vp, vp, vp, dbl, i32, P(i32), P(dbl), vp, C.c_size_t, vp]),
         }

@@ -1,4 +1,5 @@
 // Context management and the GPU VectorArray backing kernels of liblrbms_sm100.
+#include <algorithm>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -190,6 +191,56 @@ extern "C" int lrbms_remap_blocks(lrbms_handle_t h, int32_t n, const lrbms_remap
   remap_blocks_kernel<<<n, 256, 0, s>>>(dd);
   LRBMS_CUDA_CHECK(h, cudaGetLastError());
   LRBMS_CUDA_CHECK(h, cudaFreeAsync(dd, s));
+  return LRBMS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+//  Peer-memory exchange of the sharded offline results: every rank stores its contiguous region of reduced blocks
+//  straight into the other GPUs' staging buffers over NVLink (mapped peer pointers), or -- when the NVSwitch multicast
+//  object exists -- once into the multicast address, which the switch replicates to every GPU.  The caller orders the
+//  stores against the readers with a device-side barrier of the symmetric-memory signal pads afterwards.
+// ------------------------------------------------------------------------------------------------------
+namespace {
+struct PeerTargets {
+  unsigned long long dst[LRBMS_MAX_PEERS];
+  int n, multicast;
+};
+
+__global__ void __launch_bounds__(256) peer_push_kernel(const int4* __restrict__ src, int64_t n16, PeerTargets T) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) {
+    const int4 v = src[i];
+    if (T.multicast) {
+      asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(T.dst[0] + 16ull * (unsigned long long)i),
+                   "f"(__int_as_float(v.x)), "f"(__int_as_float(v.y)), "f"(__int_as_float(v.z)), "f"(__int_as_float(v.w))
+                   : "memory");
+    } else {
+#pragma unroll 1
+      for (int d = 0; d < T.n; ++d) *reinterpret_cast<int4*>(T.dst[d] + 16ull * (unsigned long long)i) = v;
+    }
+  }
+}
+}  // namespace
+
+extern "C" int lrbms_peer_push(lrbms_handle_t h, const void* src, int64_t n_bytes, int32_t n_dst, const uint64_t* dst_host,
+                               int32_t multicast, void* stream) {
+  LRBMS_REQUIRE(h, h && n_bytes >= 0 && n_dst >= 0 && n_dst <= LRBMS_MAX_PEERS && (n_dst == 0 || dst_host),
+                "peer_push: bad argument");
+  if (n_bytes == 0 || n_dst == 0) return LRBMS_OK;
+  LRBMS_REQUIRE(h, src && n_bytes % 16 == 0 && ((uintptr_t)src & 15) == 0, "peer_push: the region must be 16-byte aligned and sized");
+  LRBMS_REQUIRE(h, !multicast || n_dst == 1, "peer_push: a multicast push has exactly one (multicast) destination");
+  PeerTargets T{};
+  T.n = n_dst;
+  T.multicast = multicast ? 1 : 0;
+  for (int d = 0; d < n_dst; ++d) {
+    LRBMS_REQUIRE(h, dst_host[d] && (dst_host[d] & 15) == 0, "peer_push: unaligned or null destination");
+    T.dst[d] = dst_host[d];
+  }
+  LRBMS_CUDA_CHECK(h, cudaSetDevice(h->device));
+  const int64_t n16 = n_bytes / 16;
+  const int grid = (int)std::min<int64_t>((n16 + 255) / 256, (int64_t)h->sm_count * 8);
+  peer_push_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(static_cast<const int4*>(src), n16, T);
+  LRBMS_CUDA_CHECK(h, cudaGetLastError());
   return LRBMS_OK;
 }
 

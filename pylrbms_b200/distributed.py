@@ -60,16 +60,139 @@ def region_layout(pending, world):
     return offsets, starts
 
 
-def exchange_regions(buffer, starts):
+class PeerStaging:
+    """Symmetric (peer-mapped) staging buffer of the offline exchange on one NVLink / NVSwitch node.
+
+    Every rank allocates the same ``2 * capacity`` doubles with ``torch.distributed._symmetric_memory`` (CUDA VMM
+    allocations whose handles are exchanged once, at the rendezvous); afterwards each rank holds device pointers to
+    every peer's buffer and, where the fabric offers it, ONE multicast address that the NVSwitch replicates to all
+    GPUs.  An exchange is then: ``peer_push_kernel`` (this rank's region -> the same offset of every peer's staging
+    half, plain stores over NVLink or a single multicast store stream), a device-side barrier over the signal pads,
+    and a local copy of the other ranks' regions out of the staging half -- no NCCL launch on the path.
+
+    The two halves alternate: a rank can only push into half ``k % 2`` for exchange ``k + 2`` after it passed the
+    barrier of exchange ``k + 1``, which every peer reaches (in stream order) only after its copy-out of exchange
+    ``k`` -- so a fast rank never overwrites staging data a slow rank still reads.
+
+    Construction and growth are collective: all ranks must request the same capacity in the same order (they do:
+    the region layout is a global function of the plan)."""
+
+    _current = None          # one staging buffer per process, grown on demand
+    _disabled = None         # reason string once the peer path has been found unusable
+
+    def __init__(self, numel, mode):
+        import torch
+        import torch.distributed._symmetric_memory as symm
+        dist = _dist()
+        self.capacity = (int(numel) + 31) // 32 * 32
+        dev = torch.device('cuda', torch.cuda.current_device())
+        self.buf = symm.empty(2 * self.capacity, dtype=torch.float64, device=dev)
+        self.hdl = symm.rendezvous(self.buf, dist.group.WORLD)
+        self.rank, self.world = int(self.hdl.rank), int(self.hdl.world_size)
+        self.peer_ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        mc = 0
+        # two ranks: one destination either way, and plain peer stores measured faster than the multicast path
+        if mode == 'multicast' or (mode != 'unicast' and self.world > 2):
+            try:
+                mc = int(self.hdl.multicast_ptr) if self.hdl.has_multicast_support else 0
+            except (RuntimeError, AttributeError):
+                mc = 0
+        if mode == 'multicast' and not mc:
+            raise RuntimeError('LRBMS_PEER_EXCHANGE=multicast: the symmetric allocation has no multicast address')
+        self.multicast_ptr = mc
+        self.exchanges = 0
+
+    @property
+    def kind(self):
+        return 'nvswitch multicast stores' if self.multicast_ptr else 'nvlink peer stores'
+
+    @classmethod
+    def acquire(cls, numel):
+        """The process-wide staging buffer with room for ``numel`` doubles per half, or ``None`` when the peer path
+        is switched off (``LRBMS_PEER_EXCHANGE=0``), the backend is not NCCL, or symmetric memory cannot be set up
+        (the ranks agree on that with one all-reduce, so no rank is left waiting in a rendezvous)."""
+        import os
+        mode = os.environ.get('LRBMS_PEER_EXCHANGE', 'auto').lower()
+        if mode in ('0', 'off', 'no', 'false'):
+            return None
+        if cls._disabled is not None:
+            return None
+        if cls._current is not None and cls._current.capacity >= numel:
+            return cls._current
+        import torch
+        dist = _dist()
+        if dist.get_backend() != 'nccl' or not torch.cuda.is_available():
+            cls._disabled = 'process group backend is not nccl'
+            return None
+        new, why = None, ''
+        try:
+            grow = numel if cls._current is None else max(numel, 2 * cls._current.capacity)
+            new = cls(grow, mode)
+        except Exception as e:      # noqa: BLE001 -- any failure means "no peer path"; NCCL carries the exchange
+            why = f'{type(e).__name__}: {e}'
+        ok = torch.tensor([1 if new is not None else 0], dtype=torch.int32, device='cuda')
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            cls._disabled = why or 'symmetric memory unavailable on another rank'
+            cls._current = None
+            return None
+        cls._current = new
+        return new
+
+    def exchange(self, handle, buffer, starts):
+        """``buffer[starts[r]:starts[r+1]]`` of rank ``r`` -> the same slice of ``buffer`` on every rank."""
+        import ctypes as C
+        from ._lib import current_stream_ptr
+        rank, world = self.rank, self.world
+        total = int(starts[world])
+        a, b = int(starts[rank]), int(starts[rank + 1])
+        half = self.exchanges & 1
+        self.exchanges += 1
+        base = 8 * (half * self.capacity + a)
+        if self.multicast_ptr:
+            dsts = [self.multicast_ptr + base]
+        else:
+            dsts = [self.peer_ptrs[p] + base for p in range(world) if p != rank]
+        arr = (C.c_uint64 * len(dsts))(*dsts)
+        handle.check(handle.lib.lrbms_peer_push(handle.h, C.c_void_p(buffer.data_ptr() + 8 * a), 8 * (b - a), len(dsts),
+                                                C.cast(arr, C.c_void_p), 1 if self.multicast_ptr else 0,
+                                                current_stream_ptr()))
+        self.hdl.barrier(channel=0)
+        stage = self.buf[half * self.capacity: half * self.capacity + total]
+        if a > 0:
+            buffer[:a].copy_(stage[:a])
+        if b < total:
+            buffer[b:total].copy_(stage[b:total])
+
+
+def exchange_kind(numel=None):
+    """What carries the offline exchange in this process (for bench lines and logs)."""
+    if not is_distributed():
+        return 'none (one rank)'
+    st = PeerStaging._current
+    if st is not None:
+        return f'peer memory ({st.kind}) + signal-pad barrier'
+    why = f' [{PeerStaging._disabled}]' if PeerStaging._disabled else ''
+    return 'NCCL all_gather_into_tensor' + why
+
+
+def exchange_regions(buffer, starts, handle=None):
     """All-gather of disjoint contiguous regions of ``buffer`` (rank ``r`` owns ``buffer[starts[r]:starts[r+1]]``).
 
-    Equal-length regions (what ``region_layout`` produces): one in-place ``all_gather_into_tensor`` -- a single NCCL
-    collective over NVLink / NVSwitch, launch-latency-bound at these sizes (tens of MB), where eight serialised
-    broadcasts cost eight launches.  Unequal regions (foreign layouts) fall back to one broadcast per rank."""
+    With a library ``handle`` on an NCCL process group the regions travel over peer memory (``PeerStaging``: one
+    ``peer_push_kernel`` + a signal-pad barrier, no NCCL launch).  Otherwise -- equal-length regions (what
+    ``region_layout`` produces): one in-place ``all_gather_into_tensor``, a single NCCL collective over NVLink /
+    NVSwitch, launch-latency-bound at these sizes (tens of MB), where eight serialised broadcasts cost eight launches.
+    Unequal regions (foreign layouts) fall back to one broadcast per rank."""
     if not is_distributed():
         return
     dist = _dist()
     world, rank = dist.get_world_size(), dist.get_rank()
+    if handle is not None and buffer.is_cuda and int(starts[world]) <= buffer.numel():
+        staging = PeerStaging.acquire(int(starts[world]))
+        if staging is not None:
+            staging.exchange(handle, buffer, starts)
+            return
     sizes = [int(starts[r + 1]) - int(starts[r]) for r in range(world)]
     if len(set(sizes)) == 1 and sizes[0] > 0 and int(starts[world]) == buffer.numel():
         mine = buffer[int(starts[rank]):int(starts[rank + 1])]

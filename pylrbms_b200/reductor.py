@@ -448,9 +448,10 @@ class _Planner:
         self.gathers, self.scatters = [], []
 
     def exchange(self):
-        """Multi-GPU: every rank broadcasts its contiguous result region (an all-gather of disjoint reduced blocks)."""
+        """Multi-GPU: all-gather of the ranks' disjoint contiguous result regions -- over peer memory (NVLink stores or
+        NVSwitch multicast, ``distributed.PeerStaging``) on an NCCL group, one NCCL all-gather otherwise."""
         if self.world > 1:
-            exchange_regions(self.out, self.region_starts)
+            exchange_regions(self.out, self.region_starts, handle=self.h)
 
     # -- accounting for bench / roofline
     def stats(self):

@@ -44,6 +44,14 @@ def _worker(rank, world, port, result_dir):
         buf2[int(starts2[rank]):int(starts2[rank + 1])] = float(rank + 1)
         exchange_regions(buf2, starts2)
         assert torch.all(buf2[:5] == 1.0) and torch.all(buf2[5:] == 2.0)
+        # a library handle on host tensors / a gloo group: the peer-memory path must decline, the collective carries it
+        from pylrbms_b200.distributed import PeerStaging, exchange_kind
+        buf3 = torch.zeros(int(starts[-1]), dtype=torch.float64)
+        buf3[int(starts[rank]):int(starts[rank + 1])] = float(rank + 1)
+        exchange_regions(buf3, starts, handle=object())
+        for r in range(world):
+            assert torch.all(buf3[int(starts[r]):int(starts[r + 1])] == float(r + 1))
+        assert PeerStaging._current is None and exchange_kind().startswith('NCCL all_gather')
         # ---- online: eta over a global batch, sharded; max and arg-max must not depend on the sharding
         n_mu = 101
         eta_global = np.cos(np.arange(n_mu) * 0.37) ** 2
