@@ -55,8 +55,10 @@ const char* lrbms_last_error(lrbms_handle_t h);       /* h may be NULL: error of
 int lrbms_device_sm_count(lrbms_handle_t h, int* out);
 /* Run-time switches of a context (there are no environment variables in the library).
  * LRBMS_OPT_SINGLE_STREAM: 1 = offline plans launch all their kernels on the caller's stream (profiling); 0 (default) =
- * the independent launches of one plan run are spread over the caller's stream and three side streams of the context. */
-enum { LRBMS_OPT_SINGLE_STREAM = 1 };
+ * the independent launches of one plan run are spread over the caller's stream and three side streams of the context.
+ * LRBMS_OPT_PCG_MULTI_LAUNCH: 1 = lrbms_pcg_solve issues three launches per iteration; 0 (default) = 25 iterations per
+ * cooperative launch with grid-wide barriers (same arithmetic; used automatically only where the whole grid is resident). */
+enum { LRBMS_OPT_SINGLE_STREAM = 1, LRBMS_OPT_PCG_MULTI_LAUNCH = 2 };
 int lrbms_set_option(lrbms_handle_t h, int32_t option, int32_t value);
 /* Test hook: fills the shared memory of every SM with NaNs (a kernel that relied on stale shared memory being finite
  * or zero then fails its parity test instead of passing by luck). */

@@ -19,6 +19,7 @@ struct lrbms_context {
   // side streams of the offline plans: the launches of one plan run (one per tile-shape bucket) are independent, so they
   // are spread over the caller's stream and these and joined again before the plan returns (lrbms_set_option(LRBMS_OPT_SINGLE_STREAM, 1): off)
   bool streams_ready = false, single_stream = false, streams_failed = false;
+  bool single_launch_pcg_off = false;   // LRBMS_OPT_PCG_MULTI_LAUNCH: three launches per CG iteration instead of the cooperative kernel
   cudaStream_t side[kSideStreams] = {};
   cudaEvent_t ev_fork = nullptr, ev_join[kSideStreams] = {};
 };

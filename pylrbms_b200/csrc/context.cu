@@ -60,6 +60,7 @@ int lrbms_set_option(lrbms_handle_t h, int32_t option, int32_t value) {
   LRBMS_REQUIRE(h, h != nullptr, "lrbms_set_option: null handle");
   switch (option) {
     case LRBMS_OPT_SINGLE_STREAM: h->single_stream = value != 0; return LRBMS_OK;
+    case LRBMS_OPT_PCG_MULTI_LAUNCH: h->single_launch_pcg_off = value != 0; return LRBMS_OK;
     default: return lrbms_fail(h, LRBMS_ERR_INVALID, "lrbms_set_option: unknown option");
   }
 }

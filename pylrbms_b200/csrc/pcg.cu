@@ -4,12 +4,18 @@
 // through `lhs.apply_inverse(rhs, inverse_options)` (discretize_elliptic_block_swipdg.py:227-316, called from
 // reductor.py:75-78).  Here: Jacobi-preconditioned conjugate gradients on a CSR matrix resident in HBM.  All scalars
 // (alpha, beta, the inner products) stay on the device -- every CTA re-derives them from per-CTA partial sums in a fixed
-// order, so an iteration is three launches without a host round trip and the result is bit-reproducible.  The host
-// looks at the residual norm every kPcgCheck iterations only.
+// order, so an iteration needs no host round trip and the result is bit-reproducible.  kPcgCheck iterations run inside ONE
+// cooperative launch (`pcg_iterate_kernel`: the three phases of an iteration separated by grid-wide barriers, every CTA
+// keeping its rows of the matrix warm in its L1); the host looks at the residual norm between launches only.  Devices or
+// contexts without cooperative launch get the same arithmetic as three launches per iteration.
+#include <cooperative_groups.h>
+
 #include <algorithm>
 #include <cmath>
 
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -137,6 +143,102 @@ __global__ void __launch_bounds__(kPcgThreads) pcg_update_p_kernel(int n, int n_
   if (blockIdx.x == 0 && threadIdx.x == 0) { V.sc[parity ^ 1] = rz_new; V.sc[2] = rr; }
 }
 
+// ---- one cooperative launch = n_it iterations: at most one CTA of 1024 threads per SM (a grid-wide barrier costs by the
+// number of CTAs), the three phases of an iteration separated by grid-wide barriers.  Everything another CTA wrote is read
+// through L2 (__ldcg): the L1 of this SM may still hold the previous iteration's line.  The matrix itself is read-only
+// (__ldg, L1-resident across iterations: a CTA always takes the same rows).  Same recurrences as the three kernels above;
+// the sums are formed in a different (equally fixed) order: shuffle tree per warp, 32 warp sums, one value per CTA.
+constexpr int kCoopThreads = 1024;
+
+__device__ __forceinline__ double row_dot_cg(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colind,
+                                             const double* __restrict__ values, const double* x, int row, int sub) {
+  double s = 0.0;
+  const int p0 = __ldg(rowptr + row), p1 = __ldg(rowptr + row + 1);
+  for (int p = p0 + sub; p < p1; p += kLanesPerRow) s += __ldg(values + p) * __ldcg(x + __ldg(colind + p));
+#pragma unroll
+  for (int o = kLanesPerRow / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  return s;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// sum over the CTA, the same value in every thread; sh: 32 doubles
+__device__ __forceinline__ double coop_block_sum(double v, double* sh) {
+  v = warp_sum(v);
+  __syncthreads();                                       // sh may still be read from the previous call
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  return warp_sum(sh[threadIdx.x & 31]);
+}
+
+// every CTA sums all per-CTA partials (n_part <= 1024) in the same order -> the same value everywhere
+__device__ __forceinline__ double coop_all_partials(const double* part, int n_part, double* sh) {
+  return coop_block_sum(((int)threadIdx.x < n_part) ? __ldcg(part + threadIdx.x) : 0.0, sh);
+}
+
+__global__ void __launch_bounds__(kCoopThreads, 1) pcg_iterate_kernel(int n, const int32_t* __restrict__ rowptr,
+                                                                      const int32_t* __restrict__ colind,
+                                                                      const double* __restrict__ values, double* x, PcgVecs V,
+                                                                      double* part_c, int it0, int n_it) {
+  cg::grid_group grid = cg::this_grid();
+  __shared__ double sh[32];
+  const int n_part = gridDim.x;
+  const int rows_per_block = kCoopThreads / kLanesPerRow;
+  const int sub = threadIdx.x % kLanesPerRow;
+  for (int k = 0; k < n_it; ++k) {
+    const int parity = (it0 + k) & 1;
+    // ---- Ap = A p; partials of p.Ap
+    {
+      double pap = 0.0;
+      for (int row0 = blockIdx.x * rows_per_block; row0 < n; row0 += gridDim.x * rows_per_block) {
+        const int row = row0 + threadIdx.x / kLanesPerRow;
+        const bool row_ok = row < n;
+        const double ap = row_dot_cg(rowptr, colind, values, V.p, row_ok ? row : 0, sub);
+        if (row_ok && sub == 0) { __stcg(V.Ap + row, ap); pap += __ldcg(V.p + row) * ap; }
+      }
+      const double sum = coop_block_sum(pap, sh);
+      if (threadIdx.x == 0) __stcg(V.part_a + blockIdx.x, sum);
+    }
+    grid.sync();
+    // ---- alpha = rz / p.Ap;  x += alpha p;  r -= alpha Ap;  z = dinv r;  partials of r.z and r.r
+    {
+      const double pap = coop_all_partials(V.part_a, n_part, sh);
+      const double rz = __ldcg(V.sc + parity);
+      const bool ok = pap > 0.0 && __ldcg(V.sc + 4) == 0.0;
+      const double alpha = ok ? rz / pap : 0.0;
+      double s_rz = 0.0, s_rr = 0.0;
+      for (int i = blockIdx.x * kCoopThreads + threadIdx.x; i < n; i += gridDim.x * kCoopThreads) {
+        __stcg(x + i, __ldcg(x + i) + alpha * __ldcg(V.p + i));
+        const double rv = __ldcg(V.r + i) - alpha * __ldcg(V.Ap + i);
+        const double zv = __ldg(V.dinv + i) * rv;
+        __stcg(V.r + i, rv);
+        __stcg(V.z + i, zv);
+        s_rz += rv * zv; s_rr += rv * rv;
+      }
+      const double a = coop_block_sum(s_rz, sh), b = coop_block_sum(s_rr, sh);
+      if (threadIdx.x == 0) { __stcg(V.part_b + blockIdx.x, a); __stcg(part_c + blockIdx.x, b); }
+      grid.sync();
+      // (after the barrier: every CTA has read sc[4] of this iteration by now)
+      if (!ok && blockIdx.x == 0 && threadIdx.x == 0 && rz != 0.0) __stcg(V.sc + 4, 1.0);   // p.Ap <= 0: not positive definite
+    }
+    // ---- beta = rz_new / rz;  p = z + beta p;  CTA 0 publishes rz_new (other parity) and r.r
+    {
+      const double rz_new = coop_all_partials(V.part_b, n_part, sh);
+      const double rr = coop_all_partials(part_c, n_part, sh);
+      const double rz = __ldcg(V.sc + parity);
+      const double beta = (rz != 0.0) ? rz_new / rz : 0.0;
+      for (int i = blockIdx.x * kCoopThreads + threadIdx.x; i < n; i += gridDim.x * kCoopThreads)
+        __stcg(V.p + i, __ldcg(V.z + i) + beta * __ldcg(V.p + i));
+      if (blockIdx.x == 0 && threadIdx.x == 0) { __stcg(V.sc + (parity ^ 1), rz_new); __stcg(V.sc + 2, rr); }
+    }
+    grid.sync();
+  }
+}
+
 inline int pcg_grid(const lrbms_context* ctx, int64_t n) {
   const int64_t want = (n + kPcgThreads / kLanesPerRow - 1) / (kPcgThreads / kLanesPerRow);
   return (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)ctx->sm_count * 4));
@@ -173,6 +275,14 @@ int lrbms_pcg_solve(lrbms_handle_t h, int32_t n, const int32_t* rowptr, const in
   double* part_c = V.part_b + grid;
   double* part_d = part_c + grid;
   V.sc = part_d + grid;
+  // cooperative path: one CTA of 1024 threads per SM at most (the whole grid must be resident for the grid-wide barriers)
+  int coop_attr = 0, per_sm = 0;
+  const bool cooperative = !h->single_launch_pcg_off &&
+                           cudaDeviceGetAttribute(&coop_attr, cudaDevAttrCooperativeLaunch, h->device) == cudaSuccess && coop_attr &&
+                           cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pcg_iterate_kernel, kCoopThreads, 0) == cudaSuccess &&
+                           per_sm >= 1;
+  const int coop_grid = (int)std::max<int64_t>(1, std::min<int64_t>(((int64_t)n * kLanesPerRow + kCoopThreads - 1) / kCoopThreads,
+                                                                     std::min<int64_t>(h->sm_count, grid)));
   pcg_init_kernel<<<grid, kPcgThreads, 0, s>>>(n, rowptr, colind, values, b, x, V, part_d);
   pcg_init_scalars_kernel<<<1, kPcgThreads, 0, s>>>(grid, V, part_d);
   double sc[5] = {0, 0, 0, 0, 0};
@@ -188,7 +298,15 @@ int lrbms_pcg_solve(lrbms_handle_t h, int32_t n, const int32_t* rowptr, const in
       return lrbms_fail(h, LRBMS_ERR_NOT_SPD, "pcg_solve: p^T A p <= 0, the neighbourhood operator is not positive definite");
     }
     if (relres <= rtol || it >= max_iter) break;
-    const int n_it = std::min(kPcgCheck, max_iter - it);
+    int n_it = std::min(kPcgCheck, max_iter - it);
+    if (cooperative) {
+      int it0 = it;
+      void* args[] = {(void*)&n, (void*)&rowptr, (void*)&colind, (void*)&values, (void*)&x, (void*)&V, (void*)&part_c,
+                      (void*)&it0, (void*)&n_it};
+      LRBMS_CUDA_CHECK(h, cudaLaunchCooperativeKernel((const void*)pcg_iterate_kernel, dim3(coop_grid), dim3(kCoopThreads), args, 0, s));
+      it += n_it;
+      continue;
+    }
     for (int k = 0; k < n_it; ++k, ++it) {
       const int parity = it & 1;
       pcg_spmv_kernel<<<grid, kPcgThreads, 0, s>>>(n, rowptr, colind, values, V);

@@ -37,9 +37,25 @@ class DeviceCsr:
         self._T = None
         self._symmetric = None
 
+    @classmethod
+    def from_device(cls, rowptr, colind, values, shape):
+        """Wrap CSR arrays that already live in HBM (int32 ``rowptr`` / ``colind`` with sorted column indices, float64
+        ``values``); the host copy is made only if somebody asks for it."""
+        self = cls.__new__(cls)
+        self.shape = tuple(int(s) for s in shape)
+        self.nnz = int(values.numel())
+        self.rowptr, self.colind, self.values = rowptr, colind, values
+        self._host = None
+        self._T = None
+        self._symmetric = None
+        return self
+
     @property
     def host(self):
         """The host CSR this was uploaded from (kept for the transposed upload and for inspection)."""
+        if self._host is None:
+            self._host = sp.csr_matrix((self.values.cpu().numpy(), self.colind.cpu().numpy(), self.rowptr.cpu().numpy()),
+                                       shape=self.shape)
         return self._host
 
     @property

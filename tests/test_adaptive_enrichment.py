@@ -77,6 +77,17 @@ def test_pcg_matches_sparse_direct_solve(handle):
     # warm start from the solution: nothing left to do
     x2, iters2, _ = pcg_solve(DeviceCsr(A), torch.from_numpy(b).cuda(), x0=x, rtol=1e-12)
     assert iters2 == 0 and torch.equal(x2, x)
+    # the cooperative kernel (25 iterations per launch, grid-wide barriers) and three launches per iteration run the
+    # same recurrences: same iteration count, same solution to rounding, both reproducible bit for bit
+    x_again, iters_again, _ = pcg_solve(DeviceCsr(A), torch.from_numpy(b).cuda(), rtol=1e-13)
+    assert iters_again == iters and torch.equal(x_again, x)
+    handle.check(handle.lib.lrbms_set_option(handle.h, 2, 1))          # LRBMS_OPT_PCG_MULTI_LAUNCH
+    try:
+        x3, iters3, relres3 = pcg_solve(DeviceCsr(A), torch.from_numpy(b).cuda(), rtol=1e-13)
+    finally:
+        handle.check(handle.lib.lrbms_set_option(handle.h, 2, 0))
+    assert relres3 <= 1e-13 and abs(iters3 - iters) <= 25
+    assert np.abs(x3.cpu().numpy() - x.cpu().numpy()).max() <= 1e-11 * np.abs(x_ref).max()
     # an indefinite matrix is reported, not silently "solved"
     from pylrbms_b200._lib import LrbmsError
     with pytest.raises(LrbmsError):

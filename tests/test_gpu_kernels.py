@@ -281,6 +281,43 @@ def test_project_all_zero_operator(handle):
 
 
 # ------------------------------------------------------------------------------------------------------------
+#  peer-memory exchange kernel (one GPU: the "peers" are local buffers; tools/check_peer_exchange.py is the
+#  multi-GPU check against NCCL)
+# ------------------------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize('n_doubles,n_dst', [(32, 1), (1120, 7), (700_128, 3), (2_800_128, 7)])
+def test_peer_push_copies_region_to_every_destination(handle, n_doubles, n_dst):
+    from pylrbms_b200._lib import current_stream_ptr
+    torch = _torch()
+    lib, h = handle.lib, handle.h
+    g = torch.Generator(device='cuda').manual_seed(n_doubles + n_dst)
+    src = torch.rand(n_doubles + 64, generator=g, dtype=torch.float64, device='cuda')
+    dsts = [torch.full((n_doubles + 64,), -1.0, dtype=torch.float64, device='cuda') for _ in range(n_dst)]
+    off = 32                                                     # regions start at multiples of 32 doubles
+    arr = (C.c_uint64 * n_dst)(*[t.data_ptr() + 8 * off for t in dsts])
+    handle.check(lib.lrbms_peer_push(h, C.c_void_p(src.data_ptr() + 8 * off), 8 * n_doubles, n_dst, C.cast(arr, C.c_void_p), 0,
+                                     current_stream_ptr()))
+    torch.cuda.synchronize()
+    for t in dsts:
+        assert torch.equal(t[off:off + n_doubles], src[off:off + n_doubles])
+        assert bool((t[:off] == -1.0).all()) and bool((t[off + n_doubles:] == -1.0).all())   # nothing outside the region
+
+
+def test_peer_push_rejects_bad_arguments(handle):
+    from pylrbms_b200._lib import LrbmsError, current_stream_ptr
+    torch = _torch()
+    lib, h = handle.lib, handle.h
+    buf = torch.zeros(256, dtype=torch.float64, device='cuda')
+    arr = (C.c_uint64 * 2)(buf.data_ptr(), buf.data_ptr() + 1024)
+    for n_bytes, n_dst, multicast, src_off in [(24, 1, 0, 0), (64, 17, 0, 0), (64, 2, 1, 0), (64, 1, 0, 8)]:
+        with pytest.raises(LrbmsError):
+            handle.check(lib.lrbms_peer_push(h, C.c_void_p(buf.data_ptr() + src_off), n_bytes, n_dst, C.cast(arr, C.c_void_p),
+                                             multicast, current_stream_ptr()))
+    # an empty push is a no-op
+    handle.check(lib.lrbms_peer_push(h, C.c_void_p(buf.data_ptr()), 0, 1, C.cast(arr, C.c_void_p), 0, current_stream_ptr()))
+
+
+# ------------------------------------------------------------------------------------------------------------
 #  online: solve / estimate against dense NumPy
 # ------------------------------------------------------------------------------------------------------------
 

@@ -30,9 +30,27 @@ for mu in (0.3, 0.7, 0.5):
         it_corr[0] += d.last_local_correction_info['iterations']
         return out
     d.solve_for_local_correction = timed
+    # Gram-Schmidt extension and re-projection, timed the same way
+    t_gs = [0.0]; n_gs = [0]; t_red = [0.0]
+    orig_gs, orig_reduce = red.extend_basis_local, red.reduce
+    def timed_gs(*a, **k):
+        torch.cuda.synchronize(); t = time.perf_counter()
+        out = orig_gs(*a, **k)
+        torch.cuda.synchronize(); t_gs[0] += time.perf_counter() - t; n_gs[0] += 1
+        return out
+    def timed_reduce(*a, **k):
+        torch.cuda.synchronize(); t = time.perf_counter()
+        out = orig_reduce(*a, **k)
+        torch.cuda.synchronize(); t_red[0] += time.perf_counter() - t
+        return out
+    red.extend_basis_local, red.reduce = timed_gs, timed_reduce
     U, rd, _ = ae.solve(mu, enrichment_steps=1, callback=lambda rd_, U_, mu_, info: info_log.append(info))
     torch.cuda.synchronize(); t1 = time.perf_counter()
     d.solve_for_local_correction = orig
+    del red.extend_basis_local, red.reduce
+    print('          of which: %d Gram-Schmidt extensions %.4f s; incremental re-projection (reduce()) %.3f s; rest (two reduced '
+          'solves + estimates with their plan creation, marking, neighbourhood assembly) %.3f s'
+          % (n_gs[0], t_gs[0], t_red[0], (t1 - t0) - t_corr[0] - t_gs[0] - t_red[0]))
     print('mu %.2f: one enrichment step %.3f s wall; %d corrector solves %.3f s (%d CG iterations, neighbourhood systems of up to '
           '%d dofs); eta %.4e -> %.4e; n_red %d -> %d' % (mu, t1 - t0, n_corr[0], t_corr[0], it_corr[0],
           d.last_local_correction_info['size'], info_log[0]['eta'], info_log[-1]['eta'], info_log[0]['global RB size'],
