@@ -1,0 +1,10 @@
+#!/bin/bash
+# quick solve_kernel_v2 experiment cycle: C2 bench line with its parity gate, a few kernel tests
+mkdir -p gpurun_out
+timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-offline --no-c5 > gpurun_out/w_bench.log 2>&1; echo "bench rc=$?"
+grep -a '^{' gpurun_out/w_bench.log | tail -1 | python -c "
+import json,sys
+l=json.loads(sys.stdin.read()); r=l['roofline']
+print('value',l['value'],'ms_per_step',l['ms_per_step'],'kernel',r['kernel'],'ms_per_launch',r['ms_per_launch'],'frac',r['frac'],'exec_frac',r.get('executed_frac'),'parity',l['parity']['max_rel'])"
+tail -2 gpurun_out/w_bench.log | cut -c1-200
+timeout 600 python -m pytest tests/test_gpu_kernels.py -m gpu -x -q -k "reproducible or barrier_schedule or indefinite" 2>&1 | tail -3
