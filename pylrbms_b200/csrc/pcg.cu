@@ -5,7 +5,7 @@
 // reductor.py:75-78).  Here: Jacobi-preconditioned conjugate gradients on a CSR matrix resident in HBM.  All scalars
 // (alpha, beta, the inner products) stay on the device -- every CTA re-derives them from per-CTA partial sums in a fixed
 // order, so an iteration needs no host round trip and the result is bit-reproducible.  kPcgCheck iterations run inside ONE
-// cooperative launch (`pcg_iterate_kernel`: the three phases of an iteration separated by grid-wide barriers, every CTA
+// cooperative launch (`pcg_iterate_kernel`: two phases per iteration separated by grid-wide barriers, every CTA
 // keeping its rows of the matrix warm in its L1); the host looks at the residual norm between launches only.  Devices or
 // contexts without cooperative launch get the same arithmetic as three launches per iteration.
 #include <cooperative_groups.h>
@@ -144,21 +144,11 @@ __global__ void __launch_bounds__(kPcgThreads) pcg_update_p_kernel(int n, int n_
 }
 
 // ---- one cooperative launch = n_it iterations: at most one CTA of 1024 threads per SM (a grid-wide barrier costs by the
-// number of CTAs), the three phases of an iteration separated by grid-wide barriers.  Everything another CTA wrote is read
+// number of CTAs), the phases of an iteration separated by grid-wide barriers.  Everything another CTA wrote is read
 // through L2 (__ldcg): the L1 of this SM may still hold the previous iteration's line.  The matrix itself is read-only
 // (__ldg, L1-resident across iterations: a CTA always takes the same rows).  Same recurrences as the three kernels above;
 // the sums are formed in a different (equally fixed) order: shuffle tree per warp, 32 warp sums, one value per CTA.
 constexpr int kCoopThreads = 1024;
-
-__device__ __forceinline__ double row_dot_cg(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colind,
-                                             const double* __restrict__ values, const double* x, int row, int sub) {
-  double s = 0.0;
-  const int p0 = __ldg(rowptr + row), p1 = __ldg(rowptr + row + 1);
-  for (int p = p0 + sub; p < p1; p += kLanesPerRow) s += __ldg(values + p) * __ldcg(x + __ldg(colind + p));
-#pragma unroll
-  for (int o = kLanesPerRow / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  return s;
-}
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -180,25 +170,46 @@ __device__ __forceinline__ double coop_all_partials(const double* part, int n_pa
   return coop_block_sum(((int)threadIdx.x < n_part) ? __ldcg(part + threadIdx.x) : 0.0, sh);
 }
 
+// Two grid-wide barriers per iteration: the direction update p <- z + beta p is folded into the matrix-vector product
+// (every lane forms the entries of the new p it needs from z and the old p -- the same expression as the owner of the row,
+// so the same bits -- and the owner stores them into the OTHER p buffer, which nobody reads in this phase).
 __global__ void __launch_bounds__(kCoopThreads, 1) pcg_iterate_kernel(int n, const int32_t* __restrict__ rowptr,
                                                                       const int32_t* __restrict__ colind,
                                                                       const double* __restrict__ values, double* x, PcgVecs V,
-                                                                      double* part_c, int it0, int n_it) {
+                                                                      double* p_alt, double* part_c, int it0, int n_it) {
   cg::grid_group grid = cg::this_grid();
   __shared__ double sh[32];
   const int n_part = gridDim.x;
   const int rows_per_block = kCoopThreads / kLanesPerRow;
   const int sub = threadIdx.x % kLanesPerRow;
+  double rz_cur = __ldcg(V.sc + (it0 & 1)), rz_prev = __ldcg(V.sc + ((it0 & 1) ^ 1));
+  bool broken = __ldcg(V.sc + 4) != 0.0;
   for (int k = 0; k < n_it; ++k) {
-    const int parity = (it0 + k) & 1;
-    // ---- Ap = A p; partials of p.Ap
+    const int it = it0 + k;
+    const double* p_old = (it & 1) ? p_alt : V.p;
+    double* p_new = (it & 1) ? V.p : p_alt;
+    const double beta = (it == 0 || rz_prev == 0.0) ? 0.0 : rz_cur / rz_prev;
+    // ---- p_new = z + beta p_old (own rows stored);  Ap = A p_new;  partials of p_new.Ap
     {
       double pap = 0.0;
       for (int row0 = blockIdx.x * rows_per_block; row0 < n; row0 += gridDim.x * rows_per_block) {
         const int row = row0 + threadIdx.x / kLanesPerRow;
         const bool row_ok = row < n;
-        const double ap = row_dot_cg(rowptr, colind, values, V.p, row_ok ? row : 0, sub);
-        if (row_ok && sub == 0) { __stcg(V.Ap + row, ap); pap += __ldcg(V.p + row) * ap; }
+        const int r = row_ok ? row : 0;
+        double s = 0.0;
+        const int q0 = __ldg(rowptr + r), q1 = __ldg(rowptr + r + 1);
+        for (int q = q0 + sub; q < q1; q += kLanesPerRow) {
+          const int c = __ldg(colind + q);
+          s += __ldg(values + q) * (__ldcg(V.z + c) + beta * __ldcg(p_old + c));
+        }
+#pragma unroll
+        for (int o = kLanesPerRow / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (row_ok && sub == 0) {
+          const double pv = __ldcg(V.z + row) + beta * __ldcg(p_old + row);
+          __stcg(p_new + row, pv);
+          __stcg(V.Ap + row, s);
+          pap += pv * s;
+        }
       }
       const double sum = coop_block_sum(pap, sh);
       if (threadIdx.x == 0) __stcg(V.part_a + blockIdx.x, sum);
@@ -207,12 +218,12 @@ __global__ void __launch_bounds__(kCoopThreads, 1) pcg_iterate_kernel(int n, con
     // ---- alpha = rz / p.Ap;  x += alpha p;  r -= alpha Ap;  z = dinv r;  partials of r.z and r.r
     {
       const double pap = coop_all_partials(V.part_a, n_part, sh);
-      const double rz = __ldcg(V.sc + parity);
-      const bool ok = pap > 0.0 && __ldcg(V.sc + 4) == 0.0;
-      const double alpha = ok ? rz / pap : 0.0;
+      const bool ok = pap > 0.0 && !broken;
+      const double alpha = ok ? rz_cur / pap : 0.0;
+      if (!ok && rz_cur != 0.0) broken = true;                // p.Ap <= 0: not positive definite (the same in every CTA)
       double s_rz = 0.0, s_rr = 0.0;
       for (int i = blockIdx.x * kCoopThreads + threadIdx.x; i < n; i += gridDim.x * kCoopThreads) {
-        __stcg(x + i, __ldcg(x + i) + alpha * __ldcg(V.p + i));
+        __stcg(x + i, __ldcg(x + i) + alpha * __ldcg(p_new + i));
         const double rv = __ldcg(V.r + i) - alpha * __ldcg(V.Ap + i);
         const double zv = __ldg(V.dinv + i) * rv;
         __stcg(V.r + i, rv);
@@ -221,21 +232,19 @@ __global__ void __launch_bounds__(kCoopThreads, 1) pcg_iterate_kernel(int n, con
       }
       const double a = coop_block_sum(s_rz, sh), b = coop_block_sum(s_rr, sh);
       if (threadIdx.x == 0) { __stcg(V.part_b + blockIdx.x, a); __stcg(part_c + blockIdx.x, b); }
-      grid.sync();
-      // (after the barrier: every CTA has read sc[4] of this iteration by now)
-      if (!ok && blockIdx.x == 0 && threadIdx.x == 0 && rz != 0.0) __stcg(V.sc + 4, 1.0);   // p.Ap <= 0: not positive definite
-    }
-    // ---- beta = rz_new / rz;  p = z + beta p;  CTA 0 publishes rz_new (other parity) and r.r
-    {
-      const double rz_new = coop_all_partials(V.part_b, n_part, sh);
-      const double rr = coop_all_partials(part_c, n_part, sh);
-      const double rz = __ldcg(V.sc + parity);
-      const double beta = (rz != 0.0) ? rz_new / rz : 0.0;
-      for (int i = blockIdx.x * kCoopThreads + threadIdx.x; i < n; i += gridDim.x * kCoopThreads)
-        __stcg(V.p + i, __ldcg(V.z + i) + beta * __ldcg(V.p + i));
-      if (blockIdx.x == 0 && threadIdx.x == 0) { __stcg(V.sc + (parity ^ 1), rz_new); __stcg(V.sc + 2, rr); }
     }
     grid.sync();
+    rz_prev = rz_cur;
+    rz_cur = coop_all_partials(V.part_b, n_part, sh);
+  }
+  // publish the scalars for the host check and the next launch: rz of iteration it0 + n_it and of the one before, r.r
+  const double rr = coop_all_partials(part_c, n_part, sh);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    const int it_end = it0 + n_it;
+    __stcg(V.sc + (it_end & 1), rz_cur);
+    __stcg(V.sc + ((it_end & 1) ^ 1), rz_prev);
+    __stcg(V.sc + 2, rr);
+    if (broken) __stcg(V.sc + 4, 1.0);
   }
 }
 
@@ -244,7 +253,7 @@ inline int pcg_grid(const lrbms_context* ctx, int64_t n) {
   return (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)ctx->sm_count * 4));
 }
 
-inline size_t pcg_ws_doubles(int64_t n, int grid) { return (size_t)5 * n + (size_t)4 * grid + 8; }
+inline size_t pcg_ws_doubles(int64_t n, int grid) { return (size_t)6 * n + (size_t)4 * grid + 8; }   // r z p Ap dinv p_alt
 
 }  // namespace
 
@@ -271,7 +280,8 @@ int lrbms_pcg_solve(lrbms_handle_t h, int32_t n, const int32_t* rowptr, const in
   double* w = (double*)workspace;
   PcgVecs V;
   V.r = w; V.z = w + n; V.p = w + 2 * (size_t)n; V.Ap = w + 3 * (size_t)n; V.dinv = w + 4 * (size_t)n;
-  V.part_a = w + 5 * (size_t)n; V.part_b = V.part_a + grid;
+  double* p_alt = w + 5 * (size_t)n;                       // second direction buffer of the cooperative kernel
+  V.part_a = w + 6 * (size_t)n; V.part_b = V.part_a + grid;
   double* part_c = V.part_b + grid;
   double* part_d = part_c + grid;
   V.sc = part_d + grid;
@@ -301,8 +311,8 @@ int lrbms_pcg_solve(lrbms_handle_t h, int32_t n, const int32_t* rowptr, const in
     int n_it = std::min(kPcgCheck, max_iter - it);
     if (cooperative) {
       int it0 = it;
-      void* args[] = {(void*)&n, (void*)&rowptr, (void*)&colind, (void*)&values, (void*)&x, (void*)&V, (void*)&part_c,
-                      (void*)&it0, (void*)&n_it};
+      void* args[] = {(void*)&n, (void*)&rowptr, (void*)&colind, (void*)&values, (void*)&x, (void*)&V, (void*)&p_alt,
+                      (void*)&part_c, (void*)&it0, (void*)&n_it};
       LRBMS_CUDA_CHECK(h, cudaLaunchCooperativeKernel((const void*)pcg_iterate_kernel, dim3(coop_grid), dim3(kCoopThreads), args, 0, s));
       it += n_it;
       continue;
