@@ -1,9 +1,13 @@
 """TEST INFRASTRUCTURE ONLY -- CPU oracle, part 2: the LRBMS hot path as the reference executes it.
 
-**Parity unpinned** (see ``oracle/pymor_like.py``): there is no reference golden vector for this path and the
-reference cannot run here, so this restatement is pinned by construction only -- every function cites the
-reference lines it follows -- and the golden fixtures in ``tests/golden/`` are *its* outputs
-(``tests/golden/make_golden.py``).
+**Parity status**: the restatements of the reference's own files below (``LRBMSReductor``, ``EllipticEstimator``,
+``doerfler_marking``, ``AdaptiveEnrichment``) are **pinned** against those files themselves: ``oracle/reference_run.py``
+executes the reference's ``reductor.py`` / ``estimators.py`` / ``online_enrichment.py`` unmodified on the same seeded
+inputs, the outputs are committed as ``tests/golden/reference_run__*.npz`` and ``tests/test_oracle_golden.py`` holds this
+module to them (they agree bit for bit).  **Unpinned** remain the layers the reference gets from absent third-party
+packages: pyMOR's projection / unblock / Gram-Schmidt (``oracle/pymor_like.py``, ``GenericRBSystemReductor`` here) and the
+dune-gdt assembly behind ``build_discretization`` / ``solve_for_local_correction``.  Every function cites the reference
+lines it follows; ``tests/golden/<case>.npz`` are this module's own outputs (``tests/golden/make_golden.py``).
 
 Restated here:
 

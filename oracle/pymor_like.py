@@ -1,10 +1,13 @@
 """TEST INFRASTRUCTURE ONLY -- CPU oracle, part 1: the VectorArray / Operator algebra the reference runs on.
 
-**Parity unpinned**: the reference's own tests hold no golden vector for this path and
-the pyMOR fork + DUNE it executes on cannot be installed here.  This file restates, in plain NumPy/SciPy, the
-*published* pyMOR-0.5 semantics the reference relies on and is anchored on
-the reference's call sites, which are cited per function.  Only ``tests/``, ``__graft_entry__.smoke()`` and
-``bench.py``'s CPU-baseline legs may import it; the product package never does.
+**Parity status**: the reference's own tests hold no golden vector for this path and the pyMOR
+fork + DUNE it executes on cannot be installed here.  This file restates, in plain NumPy/SciPy, the *published* pyMOR-0.5
+semantics the reference relies on and is anchored on the reference's call sites, which
+are cited per function -- **this layer stays unpinned** (a third-party dependency absent from ``/root/reference``).  The
+reference's OWN files for the path are pinned: ``oracle/reference_run.py`` executes ``estimators.py`` / ``reductor.py`` /
+``online_enrichment.py`` unmodified on top of this layer and their outputs are committed as
+``tests/golden/reference_run__*.npz``.  Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline legs
+may import this file; the product package never does.
 
 Array convention (Appendix A.1): a VectorArray of length L in a space of dimension n is an ``(L, n)`` array.
 """

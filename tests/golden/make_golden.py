@@ -2,10 +2,11 @@
 
     python tests/golden/make_golden.py
 
-The reference (pyMOR fork + dune-gdt) cannot be imported or built in this environment and its own tests pin no
-result of the hot path, so these vectors are *oracle* outputs on seeded synthetic inputs:
-they freeze the oracle (``tests/test_oracle_golden.py`` re-derives them on the CPU) and give the CUDA path a
-fixed target (``tests/test_gpu_golden.py``).  Parity with the reference itself stays "unpinned".
+The reference's third-party layers (pyMOR fork, dune-gdt) cannot be imported or built in this environment and its own
+tests pin no result of the hot path, so these vectors are *oracle* outputs on seeded synthetic
+inputs: they freeze the oracle (``tests/test_oracle_golden.py`` re-derives them on the CPU) and give the CUDA path a
+fixed target (``tests/test_gpu_golden.py``).  The companion ``make_reference_golden.py`` produces the same quantities by
+executing the reference's own ``estimators.py`` / ``reductor.py`` / ``online_enrichment.py`` (``reference_run__*.npz``).
 """
 import hashlib
 import os

@@ -1,4 +1,6 @@
-"""The CUDA path against the committed golden vectors (tests/golden/*.npz, oracle outputs on seeded inputs)."""
+"""The CUDA path against the committed golden vectors on seeded inputs: ``tests/golden/<case>.npz`` (oracle outputs) and
+``tests/golden/reference_run__<case>.npz`` (outputs of the reference's own estimators.py / reductor.py, executed unmodified on
+NumPy stand-ins for their third-party layers -- ``oracle/reference_run.py``)."""
 import os
 import sys
 
@@ -13,15 +15,17 @@ import make_golden  # noqa: E402
 RTOL = 1e-10
 
 
+@pytest.mark.parametrize('source', ['', 'reference_run__'])
 @pytest.mark.parametrize('name', sorted(make_golden.CASES))
-def test_cuda_path_reproduces_golden(handle, name):
+def test_cuda_path_reproduces_golden(handle, name, source):
     from pylrbms_b200 import LRBMSReductor, discretize
     from pylrbms_b200.operators import LincombOperator
-    gold = np.load(os.path.join(HERE, 'golden', name + '.npz'))
+    gold = np.load(os.path.join(HERE, 'golden', source + name + '.npz'))
     data, bases = make_golden.build_case(name)
     assert make_golden.input_digest(data, bases) == str(gold['input_sha256'])
     S = data.num_subdomains
-    rd = LRBMSReductor(discretize(data)[0], bases={'domain_%d' % i: bases[i] for i in range(S)}).reduce()
+    red = LRBMSReductor(discretize(data)[0], bases={'domain_%d' % i: bases[i] for i in range(S)})
+    rd = red.reduce()
     assert list(gold['block_dims']) == rd.block_dims
     checked = 0
     for key in gold.files:
@@ -36,6 +40,10 @@ def test_cuda_path_reproduces_golden(handle, name):
         assert np.abs(got - ref).max() <= RTOL * max(np.abs(ref).max(), 1e-300), key
         checked += 1
     assert checked >= 10 * S
+    for key in gold.files:                                     # Oswald / flux-reconstruction image bases (reference-run fixtures)
+        if key.startswith('basis__'):
+            a, b = red.bases[key[len('basis__'):]].to_numpy(), gold[key]
+            assert a.shape == b.shape and np.abs(a - b).max() <= 1e-13 * max(1.0, np.abs(b).max()), key
     mus = gold['mus']
     U, eta, parts, ind = rd.sweep(mus, decompose=True)
     for k in range(len(mus)):                                  # energy norm of the assembled reduced operator, 1e-10
