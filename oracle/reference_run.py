@@ -150,7 +150,7 @@ def load_reference(reference_dir=REFERENCE_DIR):
     return out
 
 
-def build_reference_objects(data, bases, order=None):
+def build_reference_objects(data, bases, order=None, energy_products=False):
     """The oracle's operator dictionary (host-assembled inputs) with the REFERENCE's estimator and reductor on top."""
     from . import lrbms_oracle as O
     ref = load_reference()
@@ -162,8 +162,9 @@ def build_reference_objects(data, bases, order=None):
                                            oe.oswald_interpolation_error, mpi_comm=None)
     d = d.with_(estimator=est)
     S = data.num_subdomains
+    products = [d.operators['local_energy_dg_product_%d' % i] for i in range(S)] if energy_products else None
     red = ref.reductor.LRBMSReductor(d, bases=None if bases is None else {'domain_%d' % i: bases[i] for i in range(S)},
-                                     order=order)
+                                     products=products, order=order)
     return ref, d, red
 
 
@@ -205,3 +206,23 @@ def reference_enrichment(data, bases, mu, enrichment_steps, theta=0.5, max_age=2
     return {'eta': np.array([l[0] for l in log]), 'rb_size': np.array([l[1] for l in log]),
             'local_problem_solves': np.array([l[2] for l in log]), 'U': np.asarray(U.data[0]),
             'block_dims': np.array(rd.block_dims)}
+
+
+def reference_enrichment_sequence(data, mus, theta=0.5, max_age=2, target_error=1e-12):
+    """The enrichment scenario of ``tests/test_adaptive_enrichment.py``: bases initialised with the order-0 DG shape
+    functions (``reductor.py:24-30``), local energy products for the Gram-Schmidt extension, ONE enrichment step per
+    parameter of ``mus`` with the reference's ``AdaptiveEnrichment`` (``online_enrichment.py:63-93``) and ``enrich_local``
+    (``reductor.py:75-78``).  The corrector problem itself is the oracle's restatement of the dune-gdt neighbourhood solve."""
+    ref, d, red = build_reference_objects(data, None, order=0, energy_products=True)
+    block_space = types.SimpleNamespace(num_blocks=data.num_subdomains)
+    ae = ref.online_enrichment.AdaptiveEnrichment(None, d, block_space, red, red.reduce(), target_error, theta, max_age)
+    log = []
+    U = rd = None
+    for mu in mus:
+        U, rd, _ = ae.solve(mu, enrichment_steps=1,
+                            callback=lambda rd_, U_, mu_, info: log.append((float(info['eta']), int(info['global RB size']),
+                                                                            int(info['local_problem_solves']))))
+    u_fine = np.concatenate([b.data[0] for b in red.reconstruct(U)._blocks])
+    return {'mus': np.asarray(mus, dtype=float), 'eta': np.array([l[0] for l in log]), 'rb_size': np.array([l[1] for l in log]),
+            'local_problem_solves': np.array([l[2] for l in log]), 'block_dims': np.array(rd.block_dims),
+            'u_fine': u_fine, 'args': np.array([theta, max_age, target_error])}

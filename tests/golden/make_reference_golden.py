@@ -54,7 +54,34 @@ def generate(name):
     return out
 
 
+SEQUENCE_CASES = {
+    # name: (subdomains, cells, SPE10-like field seed, contrast, parameters): a field without symmetries -- on the symmetric
+    # OS2015 example mirror-image subdomains have equal indicators and the marking hangs on the last bit of the estimator
+    'enrichment_spe10like_2x2': ((2, 2), 4, 7, 50.0, (0.4, 0.9, 0.15)),
+    'enrichment_spe10like_3x3': ((3, 3), 4, 7, 50.0, (0.4, 0.9, 0.15)),
+}
+
+
+def build_sequence_case(name):
+    from pylrbms_b200.swipdg_fixture import assemble_block_swipdg, spe10_like_problem
+    subdomains, cells, seed, contrast, mus = SEQUENCE_CASES[name]
+    return assemble_block_swipdg(subdomains, cells, problem=spe10_like_problem(seed=seed, contrast=contrast)), mus
+
+
+def generate_sequence(name):
+    from oracle.reference_run import reference_enrichment_sequence
+    data, mus = build_sequence_case(name)
+    out = reference_enrichment_sequence(data, mus)
+    out.update(reference_file_digests())
+    return out
+
+
 def main():
+    for name in SEQUENCE_CASES:
+        out = generate_sequence(name)
+        path = os.path.join(HERE, 'reference_run__' + name + '.npz')
+        np.savez_compressed(path, **out)
+        print(name, '->', path, os.path.getsize(path), 'bytes', out['eta'], out['rb_size'])
     for name in make_golden.CASES:
         out = generate(name)
         path = os.path.join(HERE, 'reference_run__' + name + '.npz')

@@ -143,6 +143,66 @@ def test_adaptive_enrichment_matches_oracle(handle, num_subdomains, cells):
     assert d.last_local_correction_info['relative_residual'] <= 1e-13
 
 
+def _sequence_fixture(name):
+    import os
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.join(here, 'golden'))
+    import make_reference_golden as M
+    gold = np.load(os.path.join(here, 'golden', 'reference_run__' + name + '.npz'))
+    data, mus = M.build_sequence_case(name)
+    assert list(mus) == list(gold['mus'])
+    return gold, data, mus
+
+
+@pytest.mark.parametrize('name', ['enrichment_spe10like_2x2', 'enrichment_spe10like_3x3'])
+def test_oracle_enrichment_matches_reference_run(name):
+    """The oracle's enrichment loop against the committed run of the REFERENCE's ``AdaptiveEnrichment`` / ``enrich_local``
+    (``oracle/reference_run.py``; order-0 shape-function bases, energy products, one step per parameter)."""
+    from oracle import lrbms_oracle as O
+    gold, data, mus = _sequence_fixture(name)
+    S = data.num_subdomains
+    d = O.build_discretization(data)
+    red = O.LRBMSReductor(d, products=[d.operators['local_energy_dg_product_%d' % i] for i in range(S)], order=0)
+    theta, max_age, target = gold['args']
+    ae = O.AdaptiveEnrichment(None, d, d.solution_space, red, red.reduce(), float(target), float(theta), int(max_age))
+    log = []
+    for mu in mus:
+        U, rd, _ = ae.solve(mu, enrichment_steps=1, callback=lambda rd_, U_, mu_, info: log.append(info))
+    assert [l['global RB size'] for l in log] == list(gold['rb_size'])
+    assert [l['local_problem_solves'] for l in log] == list(gold['local_problem_solves'])
+    assert np.abs(np.array([l['eta'] for l in log]) - gold['eta']).max() <= 1e-12 * np.abs(gold['eta']).max()
+    assert list(rd.block_dims) == list(gold['block_dims'])
+    u_fine = np.concatenate([b.data[0] for b in red.reconstruct(U)._blocks])
+    assert np.abs(u_fine - gold['u_fine']).max() <= 1e-12 * np.abs(gold['u_fine']).max()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name', ['enrichment_spe10like_2x2', 'enrichment_spe10like_3x3'])
+def test_adaptive_enrichment_matches_reference_run(handle, name):
+    """The CUDA enrichment loop (``AdaptiveEnrichment.solve`` -> ``enrich_local`` -> ``lrbms_pcg_solve`` -> Gram-Schmidt ->
+    incremental ``reduce``) against the committed run of the reference's own loop on the same inputs."""
+    from pylrbms_b200 import LRBMSReductor, discretize
+    from pylrbms_b200.online_enrichment import AdaptiveEnrichment
+    gold, data, mus = _sequence_fixture(name)
+    S = data.num_subdomains
+    d, _ = discretize(data)
+    red = LRBMSReductor(d, products=[d.operators['local_energy_dg_product_%d' % i] for i in range(S)], order=0)
+    theta, max_age, target = gold['args']
+    ae = AdaptiveEnrichment(None, d, d.solution_space, red, red.reduce(), float(target), float(theta), int(max_age))
+    log = []
+    for mu in mus:
+        U, rd, _ = ae.solve(mu, enrichment_steps=1, callback=lambda rd_, U_, mu_, info: log.append(info))
+    assert [l['global RB size'] for l in log] == list(gold['rb_size'])
+    assert [l['local_problem_solves'] for l in log] == list(gold['local_problem_solves'])
+    eta = np.array([l['eta'] for l in log])
+    print('enrichment vs reference run: worst eta rel diff', np.abs(eta / gold['eta'] - 1).max())
+    assert np.abs(eta - gold['eta']).max() <= ETA_TOL * np.abs(gold['eta']).max()
+    assert list(rd.block_dims) == list(gold['block_dims'])
+    u_fine = red.reconstruct(U).to_numpy()[0]
+    assert np.abs(u_fine - gold['u_fine']).max() <= 10 * ETA_TOL * np.abs(gold['u_fine']).max()
+
+
 @pytest.mark.gpu
 def test_batched_enrichment(handle):
     """``AdaptiveEnrichment.solve_batch``: one sweep per pass over the whole parameter batch, enrichment from the worst
