@@ -558,7 +558,9 @@ def parity_gate(a, rd, mus_all, rd_ref=None):
             worst, checked = max(worst, err), checked + n
     return {'max_rel': worst, 'checked': checked, 'tol': RTOL, 'n_mu': n, 'by_quantity': {'sweep_into': e1, 'sweep': e2}, 'reduced_operators': len(rd_ref.operators) + len(rd_ref.products),
             'what': 'every reduced operator and product vs the oracle (max-norm rel.); u(mu) in the energy norm, eta, nc / r / df '
-                    'and indicators for the first {} benchmark parameters, through ReducedModel.sweep_into and .sweep'.format(n)}, rd_ref_pair
+                    'and indicators for the first {} benchmark parameters, through ReducedModel.sweep_into and .sweep'.format(n),
+            'oracle': "oracle/: restatement of the reference's reductor.py / estimators.py, bit-identical to those files executed "
+                      "unmodified on stand-ins for pyMOR / dune-gdt (oracle/reference_run.py, tests/golden/reference_run__*.npz)"}, rd_ref_pair
 
 
 def sparse_solve_gate(rd, mus, n_check=2):
