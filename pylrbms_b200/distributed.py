@@ -188,7 +188,8 @@ def exchange_regions(buffer, starts, handle=None):
         return
     dist = _dist()
     world, rank = dist.get_world_size(), dist.get_rank()
-    if handle is not None and buffer.is_cuda and int(starts[world]) <= buffer.numel():
+    aligned = buffer.data_ptr() % 16 == 0 and all(int(x) % 2 == 0 for x in starts)     # 16-byte stores in peer_push_kernel
+    if handle is not None and buffer.is_cuda and aligned and int(starts[world]) <= buffer.numel():
         staging = PeerStaging.acquire(int(starts[world]))
         if staging is not None:
             staging.exchange(handle, buffer, starts)
