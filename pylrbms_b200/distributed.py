@@ -141,10 +141,15 @@ class PeerStaging:
 
     def exchange(self, handle, buffer, starts):
         """``buffer[starts[r]:starts[r+1]]`` of rank ``r`` -> the same slice of ``buffer`` on every rank."""
+        half = self._push(handle, buffer, starts)
+        self.hdl.barrier(channel=0)
+        self._collect(buffer, starts, half)
+
+    def _push(self, handle, buffer, starts):
+        """Store this rank's region into the current staging half of every peer (or the multicast address); returns the half."""
         import ctypes as C
-        from ._lib import current_stream_ptr
+        from . import _lib
         rank, world = self.rank, self.world
-        total = int(starts[world])
         a, b = int(starts[rank]), int(starts[rank + 1])
         half = self.exchanges & 1
         self.exchanges += 1
@@ -156,8 +161,13 @@ class PeerStaging:
         arr = (C.c_uint64 * len(dsts))(*dsts)
         handle.check(handle.lib.lrbms_peer_push(handle.h, C.c_void_p(buffer.data_ptr() + 8 * a), 8 * (b - a), len(dsts),
                                                 C.cast(arr, C.c_void_p), 1 if self.multicast_ptr else 0,
-                                                current_stream_ptr()))
-        self.hdl.barrier(channel=0)
+                                                _lib.current_stream_ptr()))
+        return half
+
+    def _collect(self, buffer, starts, half):
+        """After the barrier: the other ranks' regions out of this rank's staging half."""
+        total = int(starts[self.world])
+        a, b = int(starts[self.rank]), int(starts[self.rank + 1])
         stage = self.buf[half * self.capacity: half * self.capacity + total]
         if a > 0:
             buffer[:a].copy_(stage[:a])

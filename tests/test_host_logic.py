@@ -140,3 +140,69 @@ def test_synthetic_3d_fixture_structure():
     for i, V in enumerate(bases):
         G = V @ (data.energy[i] @ V.T)
         assert np.abs(G - np.eye(len(V))).max() < 1e-10
+
+
+def test_peer_staging_offsets_and_halves(monkeypatch):
+    """The address arithmetic of the peer-memory exchange, run on host memory: three simulated ranks, the exchange kernel
+    replaced by ``memmove`` to the same destination addresses, several exchanges in a row (alternating staging halves) with
+    fresh data each time.  (The kernel itself and the real symmetric memory are covered on the GPU.)"""
+    import ctypes as C
+
+    import torch
+
+    from pylrbms_b200 import _lib
+    from pylrbms_b200.distributed import PeerStaging, region_layout
+    world = 3
+    pending = [(0, 40), (1, 70), (1, 3), (2, 11)]
+    _, starts = region_layout(pending, world)
+    total = int(starts[-1])
+    assert all(int(x) % 32 == 0 for x in starts)
+    capacity = total + 64
+    bufs = [torch.full((2 * capacity,), -7.0, dtype=torch.float64) for _ in range(world)]
+
+    class FakeLib:
+        calls = 0
+
+        @staticmethod
+        def lrbms_peer_push(h, src, n_bytes, n_dst, dst_arr, multicast, stream):
+            assert multicast == 0 and n_dst == world - 1 and n_bytes % 16 == 0
+            dsts = C.cast(dst_arr, C.POINTER(C.c_uint64))
+            for d in range(n_dst):
+                C.memmove(dsts[d], src.value, n_bytes)
+            FakeLib.calls += 1
+            return 0
+
+    class FakeHandle:
+        lib, h = FakeLib, None
+
+        @staticmethod
+        def check(rc):
+            assert rc == 0
+
+    monkeypatch.setattr(_lib, 'current_stream_ptr', lambda: C.c_void_p(0))
+    stagings = []
+    for r in range(world):
+        st = object.__new__(PeerStaging)
+        st.capacity, st.buf, st.rank, st.world = capacity, bufs[r], r, world
+        st.peer_ptrs, st.multicast_ptr, st.exchanges = [b.data_ptr() for b in bufs], 0, 0
+        stagings.append(st)
+    for it in range(5):
+        outs = []
+        for r in range(world):
+            out = torch.zeros(total, dtype=torch.float64)
+            out[int(starts[r]):int(starts[r + 1])] = torch.arange(int(starts[r + 1] - starts[r]), dtype=torch.float64) + 1000 * r + 10000 * it
+            outs.append(out)
+        halves = [stagings[r]._push(FakeHandle, outs[r], starts) for r in range(world)]
+        assert halves == [it & 1] * world
+        for r in range(world):
+            stagings[r]._collect(outs[r], starts, halves[r])
+        for r in range(1, world):
+            assert torch.equal(outs[r], outs[0])
+        for r in range(world):
+            seg = outs[0][int(starts[r]):int(starts[r + 1])]
+            assert seg[0] == 1000 * r + 10000 * it and seg[-1] == seg[0] + len(seg) - 1
+    assert FakeLib.calls == 5 * world
+    # a rank never writes its own staging buffer, and nothing lands outside the two halves' used parts
+    for r in range(world):
+        own = bufs[r].view(2, capacity)[:, int(starts[r]):int(starts[r + 1])]
+        assert bool((own == -7.0).all()) and bool((bufs[r].view(2, capacity)[:, total:] == -7.0).all())
