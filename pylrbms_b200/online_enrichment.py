@@ -3,7 +3,7 @@
 Drop-in for the reference's ``online_enrichment.py`` (``doerfler_marking`` ``:9-22``, ``AdaptiveEnrichment`` ``:25-93``):
 same constructor arguments, same ``solve(mu, enrichment_steps, callback)`` return value ``(U, rd, reductor)``, same
 marking rules (Doerfler on the *squared* indicators, plus every subdomain whose age exceeds ``marking_max_age``),
-same age bookkeeping.  What it calls is the GPU path: ``rd.solve`` / ``rd.estimate`` (``lrbms_online_*``),
+same age bookkeeping -- organised around a parameter batch: one ``rd.sweep`` (``lrbms_online_sweep``) per pass, then
 ``reductor.enrich_local`` -> ``d.solve_for_local_correction`` (``lrbms_pcg_solve``) -> ``extend_basis_local``
 (``lrbms_va_*``), and ``reductor.reduce()`` (the batched projection plans).
 """
@@ -30,7 +30,14 @@ def doerfler_marking(indicators, theta):
 
 
 class AdaptiveEnrichment:
-    """reference ``online_enrichment.py:25-93``."""
+    """Estimator-driven enrichment of the local bases (the role of reference ``online_enrichment.py:25-93``).
+
+    Built around a parameter BATCH: every pass is one ``rd.sweep`` over all parameters (solve + estimate + indicators in
+    one launch set), the parameter with the largest estimate drives the enrichment -- its indicators are marked (Doerfler
+    on the squared indicators plus every subdomain older than ``marking_max_age``, the reference's rules), its solution
+    feeds ``reductor.enrich_local`` on the marked subdomains (``lrbms_pcg_solve`` + Gram-Schmidt), and the model is
+    re-reduced (incrementally, if the reductor is set up for it).  ``solve(mu, ...)`` -- the reference's entry point, same
+    arguments, same ``(U, rd, reductor)`` result, same callback dictionary -- is the batch of one."""
 
     def __init__(self, grid_and_problem_data, discretization, block_space, reductor, rd,
                  target_error, marking_doerfler_theta, marking_max_age):
@@ -49,80 +56,79 @@ class AdaptiveEnrichment:
         bs = self.block_space
         return bs.num_blocks if hasattr(bs, 'num_blocks') else len(bs.subspaces)
 
-    def _enrich_once(self, U, mu, indicators, age_count):
-        marked_subdomains = set(doerfler_marking(indicators, self.marking_doerfler_theta))
-        num_dorfler_marked = len(marked_subdomains)
-        self.logger.info('marked %d/%d subdomains due to Doerfler marking', num_dorfler_marked, self._num_blocks)
-        for ii in np.where(age_count > self.marking_max_age)[0]:
-            marked_subdomains.add(int(ii))
-        self.logger.info('   and %d additionally due to age marking', len(marked_subdomains) - num_dorfler_marked)
-        for ii in sorted(marked_subdomains):        # sorted: the reference iterates a set (order unspecified)
-            self.reductor.enrich_local(ii, U, mu)
-        self.rd = self.reductor.reduce()
-        for ii in range(self._num_blocks):
-            if ii in marked_subdomains:
-                age_count[ii] = 1
-            else:
-                age_count[ii] += 1
-        return len(marked_subdomains)
-
     def estimate(self, U, mu, decompose=False):
         return self.rd.estimate(U, mu=mu, decompose=decompose)
 
-    def solve_batch(self, mus, enrichment_steps=np.inf, callback=None):
-        """Enrichment driven by a whole parameter batch (no counterpart in the reference, which handles one ``mu`` per
-        call, ``online_enrichment.py:63-93``): every pass sweeps ALL parameters in one ``rd.sweep`` (one launch set instead
-        of ``len(mus)`` solve / estimate calls), takes the parameter with the largest estimate, marks subdomains from ITS
-        indicators (Doerfler + age, the reference's rules), enriches with ITS solution and re-reduces; it stops when the
-        largest estimate over the batch is below ``target_error``.  Returns ``(U, eta, rd, reductor)`` for the final model,
-        ``U`` / ``eta`` covering the whole batch."""
-        mus = [self.discretization.parse_parameter(mu) for mu in mus]
-        age_count = np.ones(self._num_blocks)
-        step, local_problem_solves = 1, 0
+    def mark(self, indicators, ages):
+        """Subdomains to enrich, ascending (the reference walks an unordered set): Doerfler marking of ``indicators`` united
+        with every subdomain whose age exceeds ``marking_max_age``."""
+        by_estimate = doerfler_marking(indicators, self.marking_doerfler_theta)
+        by_age = np.flatnonzero(np.asarray(ages) > self.marking_max_age)
+        self.logger.info('marked %d/%d subdomains by the estimator, %d more by age', len(by_estimate), self._num_blocks,
+                         len(set(by_age.tolist()) - set(by_estimate)))
+        return sorted(set(by_estimate) | {int(i) for i in by_age})
+
+    def _enrich(self, U, mu, indicators, ages):
+        """One enrichment of the model from the solution ``U`` (length 1) at ``mu``; returns the number of corrector solves."""
+        marked = self.mark(indicators, ages)
+        for subdomain in marked:
+            self.reductor.enrich_local(subdomain, U, mu)
+        before = self.rd.solution_space.dim
+        self.rd = self.reductor.reduce()
+        ages += 1
+        ages[marked] = 1
+        self.logger.info('%d corrector solves, reduced system %d -> %d', len(marked), before, self.rd.solution_space.dim)
+        return len(marked)
+
+    def _passes(self, mus, enrichment_steps, report, stop_when_exhausted):
+        """The loop shared by ``solve`` and ``solve_batch``: sweep, report, stop or enrich from the worst parameter."""
         from .reductor import ExtensionError
+        ages = np.ones(self._num_blocks)
+        corrector_solves = 0
+        enrichments = 0
         while True:
             U, eta, _, indicators = self.rd.sweep(mus, decompose=True)
             worst = int(np.argmax(eta))
-            if callback:
-                subs = self.reductor.d.solution_space.subspaces
-                callback(self.rd, U, mus, {'eta': eta, 'eta_max': float(eta[worst]), 'argmax': worst,
-                                           'local_problem_solves': local_problem_solves,
-                                           'global RB size': self.rd.solution_space.dim,
-                                           'local RB sizes': [len(self.reductor.bases[s.id]) for s in subs]})
-            if eta[worst] <= self.target_error or step > enrichment_steps:
-                return U, eta, self.rd, self.reductor
-            step += 1
+            subs = self.reductor.d.solution_space.subspaces
+            report(U, eta, worst, {'local_problem_solves': corrector_solves, 'global RB size': self.rd.solution_space.dim,
+                                   'local RB sizes': [len(self.reductor.bases[s.id]) for s in subs]})
+            if eta[worst] <= self.target_error:
+                self.logger.info('estimated error %g is below the target %g', eta[worst], self.target_error)
+                return U, eta
+            if enrichments >= enrichment_steps:
+                self.logger.warning('estimated error %g above target error of %g, but stopping since enrichment_steps=%s '
+                                    'reached', eta[worst], self.target_error, enrichment_steps)
+                return U, eta
+            enrichments += 1
             try:
-                local_problem_solves = self._enrich_once(U[worst], mus[worst], indicators[:, worst], age_count)
+                corrector_solves = self._enrich(U[worst], mus[worst], indicators[:, worst], ages)
             except ExtensionError:
-                return U, eta, self.rd, self.reductor        # nothing new to add for the worst parameter
+                if not stop_when_exhausted:
+                    raise                                   # the reference lets it propagate (reductor.py:78)
+                return U, eta                               # nothing new to add for the worst parameter
 
     def solve(self, mu, enrichment_steps=np.inf, callback=None):
+        """reference ``online_enrichment.py:63-93``: ``(U, rd, reductor)`` for one parameter, ``callback(rd, U, mu, info)``
+        after every solve with ``info = {'eta', 'local_problem_solves', 'global RB size', 'local RB sizes'}``.  An
+        ``ExtensionError`` of a corrector that is already in the basis propagates, as it does there."""
         mu = self.discretization.parse_parameter(mu)
-        enrichment_step = 1
-        age_count = np.ones(self._num_blocks)
-        local_problem_solves = 0
-        rb_size = self.rd.solution_space.dim
-        while True:
-            U = self.rd.solve(mu)
-            eta, _, indicators = self.estimate(U, mu=mu, decompose=True)
-            indicators = np.asarray(indicators)
-            if indicators.ndim == 2:
-                indicators = indicators[:, 0]
+
+        def report(U, eta, worst, info):
             if callback:
-                subs = self.reductor.d.solution_space.subspaces
-                callback(self.rd, U, mu, {'eta': eta, 'local_problem_solves': local_problem_solves,
-                                          'global RB size': self.rd.solution_space.dim,
-                                          'local RB sizes': [len(self.reductor.bases[s.id]) for s in subs]})
-            if eta <= self.target_error:
-                self.logger.info('estimated error %g below target error of %g, no enrichment required', eta, self.target_error)
-                return U, self.rd, self.reductor
-            if enrichment_step > enrichment_steps:
-                self.logger.warning('estimated error %g above target error of %g, but stopping since enrichment_steps=%s '
-                                    'reached', eta, self.target_error, enrichment_steps)
-                return U, self.rd, self.reductor
-            enrichment_step += 1
-            local_problem_solves = self._enrich_once(U, mu, indicators, age_count)
-            self.logger.info('added %d local basis functions, system size increase: %d --> %d',
-                             self.rd.solution_space.dim - rb_size, rb_size, self.rd.solution_space.dim)
-            rb_size = self.rd.solution_space.dim
+                callback(self.rd, U[0], mu, dict(info, eta=float(eta[0])))
+        U, _ = self._passes([mu], enrichment_steps, report, stop_when_exhausted=False)
+        return U[0], self.rd, self.reductor
+
+    def solve_batch(self, mus, enrichment_steps=np.inf, callback=None):
+        """Enrichment driven by a whole parameter batch (no counterpart in the reference, which handles one ``mu`` per
+        call): stops when the largest estimate over the batch is below ``target_error``, after ``enrichment_steps``
+        enrichments, or when the worst parameter has nothing new to add.  ``callback(rd, U, mus, info)`` gets ``eta`` for
+        the whole batch plus ``eta_max`` / ``argmax``.  Returns ``(U, eta, rd, reductor)`` for the final model, ``U`` / ``eta``
+        covering the whole batch."""
+        mus = [self.discretization.parse_parameter(mu) for mu in mus]
+
+        def report(U, eta, worst, info):
+            if callback:
+                callback(self.rd, U, mus, dict(info, eta=eta, eta_max=float(eta[worst]), argmax=worst))
+        U, eta = self._passes(mus, enrichment_steps, report, stop_when_exhausted=True)
+        return U, eta, self.rd, self.reductor
