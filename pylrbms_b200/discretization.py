@@ -15,8 +15,8 @@ from .kernels import DeviceCsr
 from .operators import (BlockDiagonalOperator, BlockOperator, BlockProjectionOperator, BlockRowOperator, Concatenation,
                         CsrOperator, FluxReconstructionOperator, LincombOperator, OswaldInterpolationErrorOperator,
                         VectorFunctional)
-from .parameters import ExpressionParameterFunctional, ProductParameterFunctional, as_functional, parse_parameter
-from .vectorarray import BlockVectorSpace, GpuVectorSpace
+from .parameters import ProductParameterFunctional, as_functional, parse_parameter
+from .vectorarray import GpuVectorSpace
 
 
 class BlockSwipdgDiscretization:

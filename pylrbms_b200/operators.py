@@ -19,7 +19,7 @@ import numpy as np
 
 from .kernels import DeviceCsr, project_once, spmm_once
 from .parameters import evaluate as _evaluate_coefficient
-from .vectorarray import BlockVectorArray, BlockVectorSpace, GpuVectorArray, GpuVectorSpace
+from .vectorarray import BlockVectorArray, BlockVectorSpace, GpuVectorSpace
 
 
 class NumpyVectorArray:

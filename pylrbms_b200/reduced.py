@@ -21,7 +21,7 @@ import numpy as np
 
 from . import _lib
 from ._lib import Handle, LrbmsError, current_stream_ptr, host_f64, host_i32, ptr
-from .parameters import ParameterFunctional, ProductParameterFunctional, as_functional, parse_parameter, parse_parameter_batch
+from .parameters import ParameterFunctional, ProductParameterFunctional, parse_parameter, parse_parameter_batch
 from .vectorarray import ReducedVectorArray
 
 

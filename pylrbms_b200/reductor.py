@@ -36,7 +36,7 @@ from .kernels import project_desc, spmm_desc
 from .operators import (BlockColumnOperator, BlockEmbeddingOperator, BlockOperator, BlockProjectionOperator,
                         BlockRowOperator, Concatenation, CsrOperator, LincombOperator, VectorFunctional)
 from .reduced import ReducedBlockOperator, ReducedFluxReconstruction, ReducedModel, ReducedOswaldInterpolation, SuperBlock
-from .vectorarray import BlockVectorArray, GpuVectorArray, GpuVectorSpace, ReducedVectorArray
+from .vectorarray import BlockVectorArray, GpuVectorArray, ReducedVectorArray
 
 
 def _torch():

@@ -16,7 +16,6 @@ import numbers
 
 import numpy as np
 
-from . import _lib
 from ._lib import Handle, current_stream_ptr, ptr, host_f64, host_i32
 
 
