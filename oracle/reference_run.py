@@ -187,6 +187,14 @@ def reference_outputs(data, bases, mus):
         e, p, i_ = rd.estimate(u, mu, decompose=True)
         U.append(u.data[0]); eta.append(e); parts.append(np.stack([x[:, 0] for x in p])); ind.append(i_[:, 0])
     out.update(U=np.array(U), eta=np.array(eta), parts=np.array(parts), indicators=np.array(ind))
+    # the same estimator code on the FINE-SCALE operators (d.estimate of the reconstructed solution, estimators.py:45-112
+    # with the grid-walking flux reconstruction / Oswald operators replaced by their matrices)
+    f_eta, f_parts, f_ind = [], [], []
+    for k, mu in enumerate(mus):
+        U_fine = red.reconstruct(rd.solve(mu))
+        e, p, i_ = d.estimate(U_fine, mu, decompose=True)
+        f_eta.append(e); f_parts.append(np.stack([x[:, 0] for x in p])); f_ind.append(i_[:, 0])
+    out.update(fine_eta=np.array(f_eta), fine_parts=np.array(f_parts), fine_indicators=np.array(f_ind))
     # Doerfler marking (online_enrichment.py:9-22) on the indicators of the first parameter
     for theta in (0.2, 0.5, 0.9, 1.0):
         out['doerfler_%g' % theta] = np.array(ref.online_enrichment.doerfler_marking(list(ind[0]), theta), dtype=np.int64)

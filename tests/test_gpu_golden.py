@@ -57,3 +57,13 @@ def test_cuda_path_reproduces_golden(handle, name, source):
         scale = max(np.abs(gp[:, kind]).max(), r_floor if kind == 1 else 0.0)
         assert np.abs(parts[kind].T - gp[:, kind]).max() <= RTOL * scale
     assert np.abs(ind.T - gold['indicators']).max() <= 10 * RTOL * np.abs(gold['indicators']).max()
+    if 'fine_eta' in gold.files:
+        # fine-scale estimator (generic operator chain on the GPU operators) on the reconstructed solutions, against the run of
+        # the reference's estimator on the fine-scale operators; cancelling residual terms -> scale of the largest part
+        d = red.d
+        for k, mu in enumerate(mus):
+            e, p, i_ = d.estimate(red.reconstruct(rd.solve(mu)), mu, decompose=True)
+            assert abs(e - gold['fine_eta'][k]) <= 10 * RTOL * abs(gold['fine_eta'][k]), (k, e, gold['fine_eta'][k])
+            got = np.stack([np.asarray(x).reshape(S, -1)[:, 0] for x in p])
+            scale = max(np.abs(gold['fine_parts'][k]).max(), r_floor)
+            assert np.abs(got - gold['fine_parts'][k]).max() <= 10 * RTOL * scale
